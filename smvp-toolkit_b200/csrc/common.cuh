@@ -1,0 +1,150 @@
+// common.cuh -- shared declarations of libsmvp_cuda (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include <cstdlib>
+#include <new>
+
+#include "../../include/smvp_cuda.h"
+
+namespace smvp
+{
+
+// ---------------------------------------------------------------- errors / bookkeeping
+extern thread_local char g_last_cuda_error[256];
+extern std::atomic<long long> g_launches;
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define SMVP_CUDA(expr)                                                   \
+    do                                                                    \
+    {                                                                     \
+        cudaError_t e__ = (expr);                                         \
+        if (e__ != cudaSuccess)                                           \
+            return ::smvp::cuda_fail(e__, #expr, __FILE__, __LINE__);     \
+    } while (0)
+
+#define SMVP_TRY(expr)        \
+    do                        \
+    {                         \
+        int rc__ = (expr);    \
+        if (rc__ != SMVP_OK)  \
+            return rc__;      \
+    } while (0)
+
+// every kernel launch goes through this so that smvp_launch_count() is a true count
+#define SMVP_LAUNCH(kernel, grid, block, smem, stream, ...)                       \
+    do                                                                            \
+    {                                                                             \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);               \
+        ::smvp::g_launches.fetch_add(1, std::memory_order_relaxed);               \
+    } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// device allocation padded so that 16-byte vector / bulk copies may over-read the tail
+template <typename T>
+static inline cudaError_t dev_alloc(T **p, int64_t n)
+{
+    size_t bytes = (size_t)(n > 0 ? n : 0) * sizeof(T);
+    bytes = ((bytes + 255) & ~(size_t)255) + 256;
+    return cudaMalloc((void **)p, bytes);
+}
+
+struct DeviceProps
+{
+    int sms;
+    int max_smem_optin;
+};
+const DeviceProps &device_props();
+
+// ---------------------------------------------------------------- primitives (scan_sort.cu)
+// exclusive prefix sum of n uint32 -> out[0..n) (out may alias in); *d_total (device, may be null) = sum
+int exclusive_scan_u32(const uint32_t *d_in, uint32_t *d_out, int64_t n, uint32_t *d_total, cudaStream_t s);
+// histogram: counts[key[i]]++  (counts pre-zeroed by the callee), keys in [0,nbins)
+int histogram_i32(const int32_t *d_keys, int64_t n, uint32_t *d_counts, int64_t nbins, cudaStream_t s);
+// stable LSD radix sort of (key, payload) pairs over the bit ranges given; returns pointers to result
+// buffers through *out_keys/*out_vals (one of the two ping-pong buffers).
+template <typename KeyT>
+int radix_sort_pairs(KeyT *keys_a, uint32_t *vals_a, KeyT *keys_b, uint32_t *vals_b, int64_t n,
+                     const int *bit_lo, const int *bit_hi, int nranges, KeyT **out_keys, uint32_t **out_vals,
+                     cudaStream_t s);
+int max_u32(const uint32_t *d_in, int64_t n, uint32_t *d_out, cudaStream_t s);
+
+// ---------------------------------------------------------------- COO order detection (coo_common.cu)
+enum InputOrder
+{
+    ORDER_NONE = 0,
+    ORDER_ROW_COL = 1,
+    ORDER_COL_ROW = 2
+};
+// validates coordinates (SMVP_E_RANGE) and reports the arrival order
+int coo_inspect(const int32_t *d_row, const int32_t *d_col, int64_t nnz, int32_t rows, int32_t cols, int *order,
+                cudaStream_t s);
+// AoS (smvp_coo, 16 B) -> SoA
+int coo_unzip(const smvp_coo *d_aos, int64_t nnz, int32_t *d_row, int32_t *d_col, double *d_val, cudaStream_t s);
+// sorting permutation of the COO: major/minor lexicographic, using the arrival order to skip work.
+// On return *d_idx (device, nnz uint32, owned by caller via cudaFree) lists source positions in sorted
+// order, or is NULL when the input already is in the requested order.
+int coo_sort_index(const int32_t *d_major, const int32_t *d_minor, int64_t nnz, int32_t n_major, int32_t n_minor,
+                   bool already_sorted, bool sorted_transposed, uint32_t **d_idx, cudaStream_t s);
+static inline int bits_for(uint32_t n) // bits needed to represent values in [0, n)
+{
+    int b = 0;
+    while (b < 32 && (n == 0 ? 0u : (uint32_t)(n - 1)) >> b)
+        b++;
+    return b;
+}
+
+constexpr int32_t EXP_NONE = (int32_t)0x80808080; // memset(0x80) pattern: "no exponent seen", below any real one
+
+} // namespace smvp
+
+// ---------------------------------------------------------------- handles
+struct smvp_csr
+{
+    int32_t rows, cols;
+    int64_t nnz;
+    int32_t *row_ptr; // [rows+1]
+    int32_t *col_ind; // [nnz]
+    double *val;      // [nnz]
+    int32_t max_row_nnz;
+    int32_t input_order;
+    int32_t auto_variant;
+    int64_t device_bytes;
+    // merge-path plan (csr_mult.cu), built lazily
+    int32_t merge_cfg;      // which template instantiation the plan was made for (-1 none)
+    int32_t merge_tiles;
+    int32_t *tile_row;      // [merge_tiles+1] rows consumed before each tile
+    int32_t *carry_row;     // [merge_tiles]
+    double *carry_val;      // [merge_tiles]
+    // scratch for the host-vector entry point
+    double *d_x, *d_y;
+};
+
+struct smvp_tjds
+{
+    int32_t rows, cols;
+    int64_t nnz;
+    int32_t ndiag;
+    int32_t ref_diag_limit;
+    int32_t input_order;
+    int32_t nslots;      // columns with at least one entry (= length of diagonal 0)
+    int32_t last_diag_len; // entries in the last jagged diagonal
+    int32_t *perm;       // [cols]   slot -> original column
+    int32_t *slot_len;   // [cols]   entries in the column at slot p (descending)
+    int32_t *start_pos;  // [ndiag+1]
+    int32_t *row_ind;    // [nnz]
+    double *val;         // [nnz]
+    double *x_perm;      // [cols]
+    int2 *seg_blocks;    // [num_seg_blocks] {segment, first slot}: work plan of the multiply (tjds_mult.cu)
+    int32_t num_seg_blocks;
+    int64_t device_bytes;
+    // deterministic variant: exact fixed-point accumulation (tjds_mult.cu)
+    int32_t *row_exp;        // [rows] ea_r + cb_r: |a_rj| < 2^ea_r, row holds <= 2^cb_r entries (aux, built lazily)
+    long long *acc;          // [2*rows] hi/lo integer accumulators
+    int32_t *x_exp;          // [1] exponent bound of max |x|
+    double *d_x, *d_y;
+};

@@ -1,0 +1,367 @@
+// synth.cu -- device-side synthetic inputs for the configurations BASELINE.json names
+// (27-point stencil, R-MAT) and the COO shard helpers of the multi-GPU path.  See include/smvp_synth.h.
+// The reference has no generator (its only input is the .mtx loader, main-cli.c:1405-1441).
+#include "common.cuh"
+#include "../../include/smvp_synth.h"
+
+namespace smvp
+{
+
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+__host__ __device__ __forceinline__ double hash_uniform(uint64_t h) // (-1, 1)
+{
+    return 2.0 * ((double)(h >> 11) * (1.0 / 9007199254740992.0)) - 1.0;
+}
+__host__ __device__ __forceinline__ double hash_value(uint64_t seed, uint32_t row, uint32_t col)
+{
+    return hash_uniform(splitmix64(seed ^ splitmix64(((uint64_t)row << 32) | (uint64_t)col)));
+}
+
+// ------------------------------------------------------------------ 27-point stencil
+__host__ __device__ __forceinline__ int span1d(int32_t i, int32_t n) { return 1 + (i > 0 ? 1 : 0) + (i < n - 1 ? 1 : 0); }
+
+__global__ void __launch_bounds__(256) stencil_count_kernel(int32_t nx, int32_t ny, int32_t nz, int64_t row_begin, int64_t nrows,
+                                                            uint32_t *__restrict__ counts)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows)
+        return;
+    const int64_t r = row_begin + i;
+    const int32_t ix = (int32_t)(r % nx), iy = (int32_t)((r / nx) % ny), iz = (int32_t)(r / ((int64_t)nx * ny));
+    counts[i] = (uint32_t)(span1d(ix, nx) * span1d(iy, ny) * span1d(iz, nz));
+}
+
+__global__ void __launch_bounds__(256) stencil_fill_kernel(int32_t nx, int32_t ny, int32_t nz, int64_t row_begin, int64_t nrows,
+                                                           const uint32_t *__restrict__ offsets, int value_mode, uint64_t seed,
+                                                           int32_t *__restrict__ row, int32_t *__restrict__ col, double *__restrict__ val)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows)
+        return;
+    const int64_t r = row_begin + i;
+    const int32_t ix = (int32_t)(r % nx), iy = (int32_t)((r / nx) % ny), iz = (int32_t)(r / ((int64_t)nx * ny));
+    int64_t o = offsets[i];
+    for (int dz = -1; dz <= 1; dz++)
+    {
+        const int32_t z = iz + dz;
+        if (z < 0 || z >= nz)
+            continue;
+        for (int dy = -1; dy <= 1; dy++)
+        {
+            const int32_t y = iy + dy;
+            if (y < 0 || y >= ny)
+                continue;
+            for (int dx = -1; dx <= 1; dx++)
+            {
+                const int32_t x = ix + dx;
+                if (x < 0 || x >= nx)
+                    continue;
+                const int64_t c = (int64_t)x + (int64_t)nx * ((int64_t)y + (int64_t)ny * z);
+                row[o] = (int32_t)i;
+                col[o] = (int32_t)c;
+                double v;
+                if (value_mode == SMVP_VAL_STENCIL)
+                    v = (c == r) ? 26.0 : -1.0;
+                else if (value_mode == SMVP_VAL_HASH)
+                    v = hash_value(seed, (uint32_t)r, (uint32_t)c);
+                else
+                    v = 1.0;
+                val[o] = v;
+                o++;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ R-MAT
+__global__ void __launch_bounds__(256) rmat_edges_kernel(int scale, int64_t nedges, double a, double ab, double abc, uint64_t seed,
+                                                         uint64_t *__restrict__ key, uint32_t *__restrict__ idx)
+{
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nedges; e += (int64_t)gridDim.x * blockDim.x)
+    {
+        const uint64_t base = splitmix64(seed ^ (uint64_t)e);
+        uint32_t r = 0, c = 0;
+        for (int l = 0; l < scale; l++)
+        {
+            const double u = (double)(splitmix64(base + (uint64_t)l) >> 11) * (1.0 / 9007199254740992.0);
+            const uint32_t rb = u >= ab ? 1u : 0u;                       // quadrants c, d -> lower half
+            const uint32_t cb = (u >= a && u < ab) || (u >= abc) ? 1u : 0u; // quadrants b, d -> right half
+            r = (r << 1) | rb;
+            c = (c << 1) | cb;
+        }
+        key[e] = ((uint64_t)r << scale) | (uint64_t)c;
+        idx[e] = (uint32_t)e;
+    }
+}
+
+__global__ void __launch_bounds__(256) unique_flag_kernel(const uint64_t *__restrict__ key, int64_t n, uint32_t *__restrict__ flag)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) rmat_compact_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ pos, int64_t n,
+                                                           int scale, int value_mode, uint64_t seed, int32_t *__restrict__ row,
+                                                           int32_t *__restrict__ col, double *__restrict__ val)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    {
+        if (i == 0 || key[i] != key[i - 1])
+        {
+            const uint32_t o = pos[i];
+            const uint32_t r = (uint32_t)(key[i] >> scale), c = (uint32_t)(key[i] & ((1ULL << scale) - 1ULL));
+            row[o] = (int32_t)r;
+            col[o] = (int32_t)c;
+            val[o] = value_mode == SMVP_VAL_HASH ? hash_value(seed, r, c) : 1.0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) vector_fill_kernel(double *__restrict__ x, int64_t n, uint64_t seed)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        x[i] = seed == 0 ? 1.0 : hash_uniform(splitmix64(seed ^ splitmix64((uint64_t)i)));
+}
+
+// ------------------------------------------------------------------ COO filter
+__global__ void __launch_bounds__(256) filter_flag_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col, int64_t n,
+                                                          int32_t rlo, int32_t rhi, int32_t clo, int32_t chi, uint32_t *__restrict__ flag)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    {
+        const int32_t r = row[i], c = col[i];
+        flag[i] = (r >= rlo && r < rhi && c >= clo && c < chi) ? 1u : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256) filter_scatter_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                                                             const double *__restrict__ val, int64_t n, int32_t rlo, int32_t rhi,
+                                                             int32_t clo, int32_t chi, int32_t rshift, int32_t cshift,
+                                                             const uint32_t *__restrict__ pos, int32_t *__restrict__ o_row,
+                                                             int32_t *__restrict__ o_col, double *__restrict__ o_val)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    {
+        const int32_t r = row[i], c = col[i];
+        if (r >= rlo && r < rhi && c >= clo && c < chi)
+        {
+            const uint32_t o = pos[i];
+            o_row[o] = r - rshift;
+            o_col[o] = c - cshift;
+            o_val[o] = val[i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) vector_add_kernel(double *__restrict__ y, const double *__restrict__ a, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = __dadd_rn(y[i], a[i]);
+}
+
+static inline unsigned grid_for(int64_t n, int per_thread = 4)
+{
+    int64_t blocks = ceil_div64(n > 0 ? n : 1, 256 * per_thread);
+    const int64_t cap = (int64_t)device_props().sms * 16;
+    if (blocks > cap)
+        blocks = cap;
+    return (unsigned)blocks;
+}
+
+} // namespace smvp
+
+using namespace smvp;
+
+static int64_t prefix1d(int32_t n, int64_t k) // sum of span1d(i, n) for i < k
+{
+    if (k <= 0)
+        return 0;
+    if (n == 1)
+        return 1;
+    return 3 * k - 1 - (k == n ? 1 : 0);
+}
+
+extern "C" int64_t smvp_synth_stencil27_prefix(int32_t nx, int32_t ny, int32_t nz, int64_t row)
+{
+    const int64_t total = (int64_t)nx * ny * nz;
+    if (row <= 0)
+        return 0;
+    if (row > total)
+        row = total;
+    const int64_t sx = prefix1d(nx, nx), sy = prefix1d(ny, ny);
+    const int32_t ix = (int32_t)(row % nx), iy = (int32_t)((row / nx) % ny);
+    const int64_t iz = row / ((int64_t)nx * ny);
+    if (iz >= nz)
+        return prefix1d(nz, nz) * sy * sx;
+    const int64_t cz = span1d((int32_t)iz, nz), cy = span1d(iy, ny);
+    return prefix1d(nz, iz) * sy * sx + cz * prefix1d(ny, iy) * sx + cz * cy * prefix1d(nx, ix);
+}
+
+extern "C" int smvp_synth_stencil27(int32_t nx, int32_t ny, int32_t nz, int64_t row_begin, int64_t row_end, int value_mode,
+                                    uint64_t seed, int32_t **d_row, int32_t **d_col, double **d_val, int64_t *nnz)
+{
+    if (!d_row || !d_col || !d_val || !nnz || nx < 1 || ny < 1 || nz < 1)
+        return SMVP_E_ARG;
+    const int64_t total = (int64_t)nx * ny * nz;
+    if (total > 0x7fffffffLL || row_begin < 0 || row_end > total || row_begin > row_end)
+        return SMVP_E_ARG;
+    const int64_t nrows = row_end - row_begin;
+    const int64_t n = smvp_synth_stencil27_prefix(nx, ny, nz, row_end) - smvp_synth_stencil27_prefix(nx, ny, nz, row_begin);
+    if (n > 0x7fffffffLL - 1024)
+        return SMVP_E_TOOBIG;
+    *nnz = n;
+    *d_row = *d_col = nullptr;
+    *d_val = nullptr;
+    uint32_t *offs = nullptr;
+    SMVP_CUDA(dev_alloc(&offs, nrows));
+    SMVP_CUDA(dev_alloc(d_row, n));
+    SMVP_CUDA(dev_alloc(d_col, n));
+    SMVP_CUDA(dev_alloc(d_val, n));
+    if (nrows > 0)
+    {
+        const unsigned blocks = (unsigned)ceil_div64(nrows, 256);
+        SMVP_LAUNCH(stencil_count_kernel, blocks, 256, 0, 0, nx, ny, nz, row_begin, nrows, offs);
+        SMVP_TRY(exclusive_scan_u32(offs, offs, nrows, nullptr, 0));
+        SMVP_LAUNCH(stencil_fill_kernel, blocks, 256, 0, 0, nx, ny, nz, row_begin, nrows, (const uint32_t *)offs, value_mode, seed,
+                    *d_row, *d_col, *d_val);
+    }
+    SMVP_CUDA(cudaDeviceSynchronize());
+    SMVP_CUDA(cudaFree(offs));
+    return SMVP_OK;
+}
+
+extern "C" int smvp_synth_rmat(int scale, int64_t nedges, double a, double b, double c, int value_mode, uint64_t seed,
+                               int32_t **d_row, int32_t **d_col, double **d_val, int64_t *nnz)
+{
+    if (!d_row || !d_col || !d_val || !nnz || scale < 1 || scale > 30 || nedges < 0 || nedges > 0x7fffffffLL - 1024)
+        return SMVP_E_ARG;
+    *d_row = *d_col = nullptr;
+    *d_val = nullptr;
+    *nnz = 0;
+    uint64_t *key_a = nullptr, *key_b = nullptr, *rk = nullptr;
+    uint32_t *idx_a = nullptr, *idx_b = nullptr, *ri = nullptr, *d_total = nullptr;
+    auto body = [&]() -> int {
+        SMVP_CUDA(dev_alloc(&key_a, nedges));
+        SMVP_CUDA(dev_alloc(&key_b, nedges));
+        SMVP_CUDA(dev_alloc(&idx_a, nedges));
+        SMVP_CUDA(dev_alloc(&idx_b, nedges));
+        SMVP_CUDA(dev_alloc(&d_total, 1));
+        if (nedges == 0)
+            return SMVP_OK;
+        SMVP_LAUNCH(rmat_edges_kernel, grid_for(nedges), 256, 0, 0, scale, nedges, a, a + b, a + b + c, seed, key_a, idx_a);
+        const int lo = 0, hi = 2 * scale;
+        SMVP_TRY(radix_sort_pairs<uint64_t>(key_a, idx_a, key_b, idx_b, nedges, &lo, &hi, 1, &rk, &ri, 0));
+        uint32_t *flag = (ri == idx_a) ? idx_b : idx_a; // the payload is not needed: reuse its spare buffer for the flags
+        SMVP_LAUNCH(unique_flag_kernel, grid_for(nedges), 256, 0, 0, (const uint64_t *)rk, nedges, flag);
+        SMVP_TRY(exclusive_scan_u32(flag, flag, nedges, d_total, 0));
+        uint32_t total = 0;
+        SMVP_CUDA(cudaMemcpy(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost));
+        *nnz = (int64_t)total;
+        SMVP_CUDA(dev_alloc(d_row, total));
+        SMVP_CUDA(dev_alloc(d_col, total));
+        SMVP_CUDA(dev_alloc(d_val, total));
+        SMVP_LAUNCH(rmat_compact_kernel, grid_for(nedges), 256, 0, 0, (const uint64_t *)rk, (const uint32_t *)flag, nedges, scale,
+                    value_mode, seed, *d_row, *d_col, *d_val);
+        SMVP_CUDA(cudaDeviceSynchronize());
+        return SMVP_OK;
+    };
+    const int rc = body();
+    cudaFree(key_a);
+    cudaFree(key_b);
+    cudaFree(idx_a);
+    cudaFree(idx_b);
+    cudaFree(d_total);
+    return rc;
+}
+
+extern "C" int smvp_synth_vector(double *d_x, int64_t n, uint64_t seed, void *stream)
+{
+    if (n < 0 || (n > 0 && !d_x))
+        return SMVP_E_ARG;
+    if (n > 0)
+        SMVP_LAUNCH(vector_fill_kernel, grid_for(n), 256, 0, (cudaStream_t)stream, d_x, n, seed);
+    SMVP_CUDA(cudaGetLastError());
+    return SMVP_OK;
+}
+
+extern "C" int smvp_coo_filter_device(const int32_t *d_row, const int32_t *d_col, const double *d_val, int64_t nnz, int32_t row_lo,
+                                      int32_t row_hi, int32_t col_lo, int32_t col_hi, int32_t row_shift, int32_t col_shift,
+                                      int32_t **o_row, int32_t **o_col, double **o_val, int64_t *o_nnz)
+{
+    if (!o_row || !o_col || !o_val || !o_nnz || nnz < 0 || (nnz > 0 && (!d_row || !d_col || !d_val)))
+        return SMVP_E_ARG;
+    *o_row = *o_col = nullptr;
+    *o_val = nullptr;
+    *o_nnz = 0;
+    uint32_t *pos = nullptr, *d_total = nullptr;
+    auto body = [&]() -> int {
+        SMVP_CUDA(dev_alloc(&pos, nnz));
+        SMVP_CUDA(dev_alloc(&d_total, 1));
+        uint32_t total = 0;
+        if (nnz > 0)
+        {
+            SMVP_LAUNCH(filter_flag_kernel, grid_for(nnz), 256, 0, 0, d_row, d_col, nnz, row_lo, row_hi, col_lo, col_hi, pos);
+            SMVP_TRY(exclusive_scan_u32(pos, pos, nnz, d_total, 0));
+            SMVP_CUDA(cudaMemcpy(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost));
+        }
+        *o_nnz = (int64_t)total;
+        SMVP_CUDA(dev_alloc(o_row, total));
+        SMVP_CUDA(dev_alloc(o_col, total));
+        SMVP_CUDA(dev_alloc(o_val, total));
+        if (nnz > 0)
+            SMVP_LAUNCH(filter_scatter_kernel, grid_for(nnz), 256, 0, 0, d_row, d_col, d_val, nnz, row_lo, row_hi, col_lo, col_hi,
+                        row_shift, col_shift, (const uint32_t *)pos, *o_row, *o_col, *o_val);
+        SMVP_CUDA(cudaDeviceSynchronize());
+        return SMVP_OK;
+    };
+    const int rc = body();
+    cudaFree(pos);
+    cudaFree(d_total);
+    return rc;
+}
+
+extern "C" int smvp_coo_histogram_device(const int32_t *d_row, const int32_t *d_col, int64_t nnz, int by_col, int32_t nkeys,
+                                         uint32_t *d_counts)
+{
+    if (nnz < 0 || nkeys < 0 || !d_counts || (nnz > 0 && (!d_row || !d_col)))
+        return SMVP_E_ARG;
+    SMVP_TRY(histogram_i32(by_col ? d_col : d_row, nnz, d_counts, nkeys, 0));
+    SMVP_CUDA(cudaDeviceSynchronize());
+    return SMVP_OK;
+}
+
+extern "C" int smvp_vector_add_device(double *d_y, const double *d_a, int64_t n, void *stream)
+{
+    if (n < 0 || (n > 0 && (!d_y || !d_a)))
+        return SMVP_E_ARG;
+    if (n > 0)
+        SMVP_LAUNCH(vector_add_kernel, grid_for(n), 256, 0, (cudaStream_t)stream, d_y, d_a, n);
+    SMVP_CUDA(cudaGetLastError());
+    return SMVP_OK;
+}
+
+extern "C" int smvp_flush_l2(int64_t bytes, void *stream)
+{
+    static thread_local void *buf = nullptr;
+    static thread_local int64_t cap = 0;
+    if (bytes <= 0)
+        return SMVP_E_ARG;
+    if (cap < bytes)
+    {
+        cudaFree(buf);
+        buf = nullptr;
+        cap = 0;
+        SMVP_CUDA(cudaMalloc(&buf, (size_t)bytes));
+        cap = bytes;
+    }
+    SMVP_CUDA(cudaMemsetAsync(buf, 0, (size_t)bytes, (cudaStream_t)stream));
+    return SMVP_OK;
+}
+
+extern "C" void smvp_device_free(void *d_ptr) { cudaFree(d_ptr); }

@@ -1,0 +1,318 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via smvp_toolkit_b200.engine) against the oracle.
+
+Bar (BASELINE.json north_star):  integer arrays bit-exact; y within 1e-12 relative L2 (fp64);
+the deterministic TJDS variant bit-identical run to run.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import synth_ref
+import util
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12  # relative L2, fp64 (north_star)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import smvp_toolkit_b200 as e
+
+    assert e.device_count() >= 1
+    return e
+
+
+def torch_view(arr):
+    import torch
+
+    return torch.as_tensor(arr, device="cuda")
+
+
+def check_csr(eng, coo, m, n, x, variants=(1, 2)):
+    rp, ci, va = oracle.csr_build(coo, m, n)
+    A = eng.CsrMatrix.build(coo, m, n)
+    g_rp, g_ci, g_va = A.export()
+    assert np.array_equal(g_rp, rp), "row_ptr not bit-exact"
+    assert np.array_equal(g_ci, ci), "col_ind not bit-exact"
+    assert np.array_equal(g_va.view(np.int64), va.view(np.int64)), "val not bit-exact"
+    y_ref = oracle.csr_mult(rp, ci, va, x)
+    for v in variants:
+        y, td = A.mult(x, iters=2, variant=v)
+        assert util.rel_l2(y, y_ref) <= TOL, "variant %d" % v
+        assert len(td.time_each) == 2 and td.time_total >= 0
+        if np.linalg.norm(y_ref) == 0:
+            assert np.all(y == 0)
+    A.free()
+    return y_ref
+
+
+def check_tjds(eng, coo, m, n, x, y_csr):
+    t = oracle.tjds_build(coo, m, n)
+    A = eng.TjdsMatrix.build(coo, m, n)
+    perm, sp, ri, va = A.export()
+    assert A.ndiag == t.ndiag
+    assert np.array_equal(perm, t.perm), "perm not bit-exact"
+    assert np.array_equal(sp, t.start_pos), "start_pos not bit-exact"
+    assert np.array_equal(ri, t.row_ind), "row_ind not bit-exact"
+    assert np.array_equal(va.view(np.int64), t.val.view(np.int64)), "val not bit-exact"
+    assert A.ref_diag_limit == t.ref_limit
+    y_ref = oracle.tjds_mult(t, x)
+    ya, _ = A.mult(x, iters=2, variant=eng.TJDS_ATOMIC)
+    yd1, _ = A.mult(x, iters=1, variant=eng.TJDS_DETERMINISTIC)
+    yd2, _ = A.mult(x, iters=3, variant=eng.TJDS_DETERMINISTIC)
+    assert util.rel_l2(ya, y_ref) <= TOL
+    assert util.rel_l2(yd1, y_ref) <= TOL
+    assert util.rel_l2(ya, y_csr) <= TOL and util.rel_l2(yd1, y_csr) <= TOL  # TJDS == CSR, pins x indexing
+    assert np.array_equal(yd1.view(np.int64), yd2.view(np.int64)), "deterministic variant differs run to run"
+    A.free()
+    return yd1
+
+
+# ---------------------------------------------------------------------------- sample matrices
+@pytest.mark.parametrize("name", util.SAMPLES)
+@pytest.mark.parametrize("xmode", ["ones", "random"])
+def test_sample_matrices(eng, name, xmode):
+    m, n, coo = util.load_sample(name)
+    x = np.ones(n) if xmode == "ones" else np.random.default_rng(7).uniform(-1, 1, n)
+    y_csr = check_csr(eng, coo, m, n, x)
+    check_tjds(eng, coo, m, n, x, y_csr)
+
+
+@pytest.mark.parametrize("name,alg", sorted(util.GOLDEN_REPORTS))
+def test_golden_reports_through_reference_interface(eng, name, alg):
+    """The reference's golden report files, through the mirrored entry points (x = ones)."""
+    rep = util.parse_report(os.path.join(util.GOLDEN, "reports", util.GOLDEN_REPORTS[(name, alg)]))
+    m, n, coo = util.load_sample(name)
+    if alg == "CSR":
+        y, td = eng.smvp_csr_compute(coo, m, len(coo), 3, fInputColumns=n)
+    else:
+        y, td = eng.smvp_tjds_compute(coo, m, n, len(coo), 3, ref_compat=True)  # the shipped truncation (U4/U5)
+    assert len(td.time_each) == 3
+    assert util.rel_l2(y, rep["y"]) <= 5e-6  # the files hold 6 significant digits
+    # per element: 6 significant digits, with an absolute floor for rows that cancel to ~0 (memplus)
+    scale = np.abs(coo["val"]).max() if len(coo) else 1.0
+    assert np.all(np.abs(y - rep["y"]) <= 5e-6 * np.abs(rep["y"]) + 1e-12 * scale * 600)
+
+
+# ---------------------------------------------------------------------------- random / edge cases
+SHAPES = [
+    (1, 1, 0), (1, 1, 1), (1, 7, 5), (7, 1, 4), (5, 5, 0), (17, 33, 100), (64, 64, 64 * 64), (300, 200, 3000),
+    (1000, 1000, 20000), (2000, 50, 7000), (50, 2000, 7000), (4096, 4096, 50000), (10000, 10000, 10001),
+]
+
+
+@pytest.mark.parametrize("m,n,nnz", SHAPES)
+@pytest.mark.parametrize("order", ["shuffled", "rowcol", "colrow"])
+def test_random_matrices(eng, m, n, nnz, order):
+    rng = np.random.default_rng(m * 1000003 + n * 101 + nnz)
+    coo = util.random_coo(rng, m, n, nnz)
+    if order == "rowcol":
+        coo = coo[np.lexsort((coo["col"], coo["row"]))]
+    elif order == "colrow":
+        coo = coo[np.lexsort((coo["row"], coo["col"]))]
+    x = rng.uniform(-3, 3, n)
+    y_csr = check_csr(eng, coo, m, n, x)
+    check_tjds(eng, coo, m, n, x, y_csr)
+
+
+def test_skewed_rows_and_columns(eng):
+    """One dense row, one dense column, many empty rows: the merge-path and segmented-TJDS cases."""
+    rng = np.random.default_rng(99)
+    m = n = 30000
+    cells = set()
+    for c in range(n):
+        cells.add((123, c))
+    for r in range(m):
+        cells.add((r, 77))
+    while len(cells) < 2 * n + 40000:
+        r = int(rng.integers(0, m // 3)) * 3  # rows not divisible by 3 stay (mostly) empty
+        cells.add((r, int(rng.integers(0, n))))
+    rc = np.array(sorted(cells), dtype=np.int64)
+    coo = oracle.make_coo(rc[:, 0], rc[:, 1], rng.uniform(-1, 1, len(rc)))
+    rng.shuffle(coo)
+    x = rng.uniform(-1, 1, n)
+    y_csr = check_csr(eng, coo, m, n, x)
+    check_tjds(eng, coo, m, n, x, y_csr)
+
+
+def test_out_of_range_and_bad_args(eng):
+    coo = oracle.make_coo([0, 5], [0, 1], [1.0, 2.0])
+    with pytest.raises(eng.SmvpError) as ei:
+        eng.CsrMatrix.build(coo, 3, 3)
+    assert ei.value.code == eng.E_RANGE
+    with pytest.raises(eng.SmvpError) as ei:
+        eng.TjdsMatrix.build(coo, 3, 3)
+    assert ei.value.code == eng.E_RANGE
+    A = eng.CsrMatrix.build(oracle.make_coo([0], [0], [1.0]), 2, 2)
+    with pytest.raises(eng.SmvpError) as ei:
+        A.mult(np.ones(2), iters=0)
+    assert ei.value.code == eng.E_ARG
+    with pytest.raises(eng.SmvpError):
+        A.mult(np.ones(2), iters=1, variant=9)
+
+
+def test_deterministic_tjds_is_exactly_rounded(eng):
+    """The fixed-point accumulation is exact: every y_r equals the correctly rounded sum of the fp64 products."""
+    rng = np.random.default_rng(5)
+    m, n, nnz = 400, 400, 20000
+    coo = util.random_coo(rng, m, n, nnz)
+    coo["val"] *= 10.0 ** rng.integers(-8, 8, nnz)  # wide dynamic range inside rows
+    x = rng.uniform(-1, 1, n) * 10.0 ** rng.integers(-3, 3, n)
+    A = eng.TjdsMatrix.build(coo, m, n)
+    y, _ = A.mult(x, 1, eng.TJDS_DETERMINISTIC)
+    exact = np.zeros(m)
+    for r in range(m):
+        sel = coo["row"] == r
+        exact[r] = math.fsum((coo["val"][sel] * x[coo["col"][sel]]).tolist())
+    ulp = np.spacing(np.abs(exact))
+    assert np.all(np.abs(y - exact) <= 2 * ulp + 1e-300)
+    A.free()
+
+
+def test_time_stats_match_oracle(eng):
+    ms = np.array([0.31, 0.29, 0.5, 0.30, 0.33])
+    td = eng.TimeData(ms)
+    s = oracle.time_stats(ms)
+    assert (td.time_total, td.time_avg, td.time_min, td.time_max) == (s["total"], s["avg"], s["min"], s["max"])
+    assert abs(td.time_stdev - s["stdev"]) <= 1e-15
+
+
+# ---------------------------------------------------------------------------- synthetic generators
+def test_stencil_generator_matches_numpy(eng):
+    import torch
+
+    nx, ny, nz = 5, 4, 3
+    for (rb, re) in [(0, None), (7, 41)]:
+        for mode in (0, 1):
+            ref = synth_ref.stencil27(nx, ny, nz, rb, re, mode, seed=11)
+            r, c, v = eng.synth_stencil27(nx, ny, nz, rb, re, mode, seed=11)
+            assert r.n == len(ref)
+            assert np.array_equal(torch_view(r).cpu().numpy(), ref["row"])
+            assert np.array_equal(torch_view(c).cpu().numpy(), ref["col"])
+            assert np.array_equal(torch_view(v).cpu().numpy(), ref["val"])
+    counts = synth_ref.stencil27_row_counts(nx, ny, nz)
+    pref = np.concatenate([[0], np.cumsum(counts)])
+    for row in range(nx * ny * nz + 1):
+        assert eng.synth_stencil27_prefix(nx, ny, nz, row) == pref[row]
+    assert eng.synth_stencil27_prefix(369, 369, 369, 369 ** 3) == 1105 ** 3  # nnz of config 3
+
+
+def test_rmat_generator_matches_numpy(eng):
+    ref = synth_ref.rmat(10, 20000, seed=42)
+    r, c, v = eng.synth_rmat(10, 20000, seed=42)
+    assert r.n == len(ref)
+    assert np.array_equal(torch_view(r).cpu().numpy(), ref["row"])
+    assert np.array_equal(torch_view(c).cpu().numpy(), ref["col"])
+    assert np.array_equal(torch_view(v).cpu().numpy(), ref["val"])
+
+
+# ---------------------------------------------------------------------------- device-resident path, medium size
+@pytest.mark.parametrize("kind", ["stencil", "rmat"])
+def test_device_path_medium(eng, kind):
+    """Device generators -> device builds -> device multiplies, against the oracle (seconds on the CPU)."""
+    import torch
+
+    if kind == "stencil":
+        nx = 48
+        m = n = nx ** 3
+        r, c, v = eng.synth_stencil27(nx, nx, nx, value_mode=eng.VAL_HASH, seed=3)
+    else:
+        scale = 17
+        m = n = 1 << scale
+        r, c, v = eng.synth_rmat(scale, 16 << scale, seed=42)
+    nnz = r.n
+    coo = oracle.make_coo(torch_view(r).cpu().numpy(), torch_view(c).cpu().numpy(), torch_view(v).cpu().numpy())
+    x = synth_ref.vector(n, 77)
+    d_x = torch.empty(n, dtype=torch.float64, device="cuda")
+    eng.synth_vector(d_x, n, 77)
+    assert np.array_equal(d_x.cpu().numpy(), x)
+    d_y = torch.empty(m, dtype=torch.float64, device="cuda")
+
+    rp, ci, va = oracle.csr_build(coo, m, n)
+    y_ref = oracle.csr_mult(rp, ci, va, x)
+    A = eng.CsrMatrix.build_device(r, c, v, m, n, nnz)
+    assert A.input_order == 1  # generators emit (row, col)-sorted lists
+    g = A.export()
+    assert np.array_equal(g[0], rp) and np.array_equal(g[1], ci) and np.array_equal(g[2], va)
+    for variant in (eng.CSR_VECTOR, eng.CSR_MERGE, eng.CSR_AUTO):
+        d_y.fill_(float("nan"))
+        A.mult_device(d_x, d_y, variant)
+        torch.cuda.synchronize()
+        assert util.rel_l2(d_y.cpu().numpy(), y_ref) <= TOL, variant
+    A.free()
+
+    t = oracle.tjds_build(coo, m, n)
+    T = eng.TjdsMatrix.build_device(r, c, v, m, n, nnz)
+    perm, sp, ri, tv = T.export()
+    assert np.array_equal(perm, t.perm) and np.array_equal(sp, t.start_pos)
+    assert np.array_equal(ri, t.row_ind) and np.array_equal(tv, t.val)
+    T.set_x_device(d_x)
+    outs = []
+    for variant in (eng.TJDS_ATOMIC, eng.TJDS_DETERMINISTIC, eng.TJDS_DETERMINISTIC):
+        d_y.fill_(float("nan"))
+        T.mult_device(d_y, variant)
+        torch.cuda.synchronize()
+        outs.append(d_y.cpu().numpy().copy())
+        assert util.rel_l2(outs[-1], y_ref) <= TOL, variant
+    assert np.array_equal(outs[1].view(np.int64), outs[2].view(np.int64))
+    T.free()
+
+
+# ---------------------------------------------------------------------------- BASELINE.json full size
+def test_full_size_stencil_properties(eng):
+    """Config 3 (27-point stencil 369^3, 1.35e9 nnz): size-independent properties, no oracle pass needed.
+       (a) x = ones with the {26,-1} values: y_r = 27 - (entries in row r), exactly;
+       (b) vector-CSR == merge-path CSR == TJDS(det) within 1e-12 on a random x;
+       (c) linearity A(2 x1 - 3 x2) = 2 A x1 - 3 A x2 within 1e-12."""
+    import torch
+
+    nx = int(os.environ.get("SMVP_TEST_GRID", "369"))
+    m = n = nx ** 3
+    r, c, v = eng.synth_stencil27(nx, nx, nx, value_mode=eng.VAL_STENCIL)
+    nnz = r.n
+    assert nnz == (3 * nx - 2) ** 3
+    A = eng.CsrMatrix.build_device(r, c, v, m, n, nnz)
+    T = eng.TjdsMatrix.build_device(r, c, v, m, n, nnz)
+    for a in (r, c, v):
+        a.free()
+    assert T.ndiag == 27
+    counts = torch.as_tensor(synth_ref.stencil27_row_counts(nx, nx, nx)).to("cuda")
+    expect = (27 - counts).to(torch.float64)
+    row_ptr = torch.as_tensor(A.export_row_ptr()).to("cuda")
+    assert torch.equal(row_ptr[1:] - row_ptr[:-1], counts.to(torch.int32))
+    x1 = torch.ones(n, dtype=torch.float64, device="cuda")
+    y = torch.empty(m, dtype=torch.float64, device="cuda")
+    for variant in (eng.CSR_VECTOR, eng.CSR_MERGE):
+        y.fill_(float("nan"))
+        A.mult_device(x1, y, variant)
+        assert torch.equal(y, expect), variant
+    T.set_x_device(x1)
+    for variant in (eng.TJDS_ATOMIC, eng.TJDS_DETERMINISTIC):
+        y.fill_(float("nan"))
+        T.mult_device(y, variant)
+        assert torch.equal(y, expect), variant
+
+    xa = torch.empty(n, dtype=torch.float64, device="cuda")
+    xb = torch.empty(n, dtype=torch.float64, device="cuda")
+    eng.synth_vector(xa, n, 1)
+    eng.synth_vector(xb, n, 2)
+    ya, yb, yc, yv = (torch.empty(m, dtype=torch.float64, device="cuda") for _ in range(4))
+    A.mult_device(xa, ya, eng.CSR_MERGE)
+    A.mult_device(xb, yb, eng.CSR_MERGE)
+    A.mult_device(2 * xa - 3 * xb, yc, eng.CSR_MERGE)
+    lin = 2 * ya - 3 * yb
+    assert float(torch.linalg.norm(yc - lin) / torch.linalg.norm(lin)) <= TOL
+    A.mult_device(xa, yv, eng.CSR_VECTOR)
+    assert float(torch.linalg.norm(yv - ya) / torch.linalg.norm(ya)) <= TOL
+    T.set_x_device(xa)
+    T.mult_device(yv, eng.TJDS_DETERMINISTIC)
+    assert float(torch.linalg.norm(yv - ya) / torch.linalg.norm(ya)) <= TOL
+    y2 = torch.empty_like(yv)
+    T.mult_device(y2, eng.TJDS_DETERMINISTIC)
+    assert torch.equal(y2, yv)
+    A.free()
+    T.free()
