@@ -1,0 +1,284 @@
+"""Multi-GPU partitioning of the CSR / TJDS path: one process per GPU, torch.distributed for the plumbing.
+
+The reference is single-process and single-threaded; the path shards naturally with
+exactly one exchange step per format:
+
+  CSR   contiguous ROW blocks balanced by nnz; x replicated; each rank multiplies its rows; the y
+        blocks are all-gathered (NCCL allgatherv over NVLink) so every rank ends with the full y.
+  TJDS  contiguous COLUMN blocks balanced by nnz; each rank builds a local TJDS over its columns and
+        needs only its slice of x; partial y vectors are combined by NCCL reduce-scatter (sum, fp64).
+
+The partition arithmetic (`balanced_bounds`) and the two operators are backend-agnostic: the
+world_size-2 gloo tests drive them on CPU with an injected local multiply.
+"""
+import json
+import os
+
+import numpy as np
+
+
+def balanced_bounds(prefix, total_keys, parts):
+    """Boundaries 0 = b_0 <= ... <= b_parts = total_keys with b_g = lower_bound(prefix, g*total/parts),
+    where prefix(k) = number of nonzeros with key < k (r_g = lower_bound(row_ptr, g*nnz/G))."""
+    total = int(prefix(total_keys))
+    bounds = [0]
+    for g in range(1, parts):
+        target = total * g // parts
+        lo, hi = bounds[-1], total_keys
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if prefix(mid) < target:
+                lo = mid + 1
+            else:
+                hi = mid
+        bounds.append(lo)
+    bounds.append(total_keys)
+    return bounds
+
+
+def bounds_from_counts(counts, parts):
+    """Same, from an explicit per-key count array (numpy int)."""
+    csum = np.concatenate([[0], np.cumsum(np.asarray(counts, dtype=np.int64))])
+    return balanced_bounds(lambda k: csum[k], len(counts), parts)
+
+
+def allgather_v(dist, y_full, bounds, rank):
+    """All-gather of uneven contiguous blocks of y_full (block g = y_full[bounds[g]:bounds[g+1]]), in place."""
+    views = [y_full[bounds[g]:bounds[g + 1]] for g in range(len(bounds) - 1)]
+    dist.all_gather(views, views[rank])
+
+
+# ------------------------------------------------------------------------------------ matrix sources
+class StencilSource:
+    """27-point stencil on an nx*ny*nz grid (BASELINE.json configs[2]); shards are generated on the device."""
+
+    def __init__(self, eng, nx, ny, nz, value_mode=None, seed=0):
+        self.eng, self.nx, self.ny, self.nz = eng, nx, ny, nz
+        self.rows = self.cols = nx * ny * nz
+        self.value_mode = eng.VAL_STENCIL if value_mode is None else value_mode
+        self.seed = seed
+        self.nnz = self.row_prefix(self.rows)
+        self.desc = "27-point stencil %dx%dx%d" % (nx, ny, nz)
+
+    def row_prefix(self, r):
+        return self.eng.synth_stencil27_prefix(self.nx, self.ny, self.nz, r)
+
+    col_prefix = row_prefix  # structurally symmetric
+
+    def row_block(self, r0, r1):
+        """(row_local, col_global, val, order) of rows [r0, r1)."""
+        return self.eng.synth_stencil27(self.nx, self.ny, self.nz, r0, r1, self.value_mode, self.seed)
+
+    def col_block(self, c0, c1):
+        """(row_global, col_local, val) of columns [c0, c1).  The {26,-1} stencil matrix is symmetric, so the
+        column block is the row block with the two index arrays swapped (it arrives (col,row)-sorted)."""
+        if self.value_mode != self.eng.VAL_STENCIL:
+            raise ValueError("col_block by symmetry needs the symmetric {26,-1} values")
+        r, c, v = self.eng.synth_stencil27(self.nx, self.ny, self.nz, c0, c1, self.value_mode, self.seed)
+        return c, r, v
+
+
+class RmatSource:
+    """R-MAT 2^scale square matrix (BASELINE.json configs[3]/[4]).  Every rank generates the same deduplicated
+    edge list on its own device (counter-based RNG) and cuts its block out of it."""
+
+    def __init__(self, eng, scale, nedges, seed=42):
+        import torch
+
+        self.eng = eng
+        self.rows = self.cols = 1 << scale
+        self.row, self.col, self.val = eng.synth_rmat(scale, nedges, seed=seed)
+        self.nnz = self.row.n
+        self.desc = "R-MAT scale %d, %d draws, %d unique" % (scale, nedges, self.nnz)
+        self._prefix = {}
+        self._torch = torch
+
+    def _csum(self, by_col):
+        if by_col not in self._prefix:
+            torch = self._torch
+            counts = torch.zeros(self.rows + 1, dtype=torch.int32, device="cuda")
+            self.eng.coo_histogram_device(self.row, self.col, self.nnz, by_col, self.rows, counts)
+            csum = torch.zeros(self.rows + 1, dtype=torch.int64, device="cuda")
+            csum[1:] = torch.cumsum(counts[:-1].to(torch.int64), 0)
+            self._prefix[by_col] = csum.cpu().numpy()
+        return self._prefix[by_col]
+
+    def row_prefix(self, r):
+        return int(self._csum(False)[r])
+
+    def col_prefix(self, c):
+        return int(self._csum(True)[c])
+
+    def row_block(self, r0, r1):
+        return self.eng.coo_filter_device(self.row, self.col, self.val, self.nnz, r0, r1, 0, self.cols, r0, 0)
+
+    def col_block(self, c0, c1):
+        return self.eng.coo_filter_device(self.row, self.col, self.val, self.nnz, 0, self.rows, c0, c1, 0, c0)
+
+    def release(self):
+        for a in (self.row, self.col, self.val):
+            a.free()
+
+
+def _measured_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture, if any."""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------ operators
+class RowBlockCsr:
+    """y = A x with A in CSR, rows cut into nnz-balanced blocks over `world` ranks."""
+
+    def __init__(self, eng, source, rank, world, variant=0, exchange="nccl"):
+        import torch
+
+        self.eng, self.rank, self.world, self.variant, self.exchange = eng, rank, world, variant, exchange
+        self.M, self.N = source.rows, source.cols
+        self.bounds = balanced_bounds(source.row_prefix, self.M, world)
+        self.r0, self.r1 = self.bounds[rank], self.bounds[rank + 1]
+        r, c, v = source.row_block(self.r0, self.r1)
+        self.local_nnz = r.n
+        self.A = eng.CsrMatrix.build_device(r, c, v, self.r1 - self.r0, self.N, r.n)
+        for a in (r, c, v):
+            a.free()
+        if hasattr(source, "release") and world == 1:
+            source.release()
+        self.global_nnz = source.nnz
+        self.global_bytes_per_mult = 12 * source.nnz + 4 * (self.M + 1) + 8 * self.N + 8 * self.M
+        self.local_bytes_per_mult = self.A.bytes_per_mult
+        self.y_full = torch.zeros(self.M, dtype=torch.float64, device="cuda")
+        self.y_local = self.y_full[self.r0:self.r1]
+        self.local_rows_out = self.r1 - self.r0
+        resolved = self.A.auto_variant if variant == eng.CSR_AUTO else variant
+        self.variant_name = {eng.CSR_VECTOR: "vector", eng.CSR_MERGE: "merge"}[resolved]
+        self.kernel_name = "csr_%s_kernel" % self.variant_name
+        self.partition_desc = ("row blocks balanced by nnz, %d ranks; x replicated; y %s" %
+                               (world, "all-gathered over NCCL" if (world > 1 and exchange == "nccl") else "kept local"))
+        self.e2e_api = ("smvp_csr_mult(A, x_host, y_host, iters=1) [C ABI, pinned host buffers]" if world == 1 else
+                        "H2D x -> smvp_csr_mult_device -> NCCL allgather -> D2H y block")
+        self.x = None
+        self._source_desc = source.desc
+
+    def set_x(self, x, stream=None):
+        self.x = x
+
+    def multiply(self, stream=None):
+        self.A.mult_device(self.x, self.y_local, self.variant, stream)
+
+    def exchange_y(self, stream=None):
+        if self.world > 1 and self.exchange == "nccl":
+            import torch.distributed as dist
+
+            allgather_v(dist, self.y_full, self.bounds, self.rank)
+
+    def step(self, stream=None):
+        self.multiply(stream)
+        self.exchange_y(stream)
+
+    def e2e_step(self, hx, hy, stream):
+        import ctypes
+
+        if self.world == 1:
+            # the reference-facing C-ABI call with host buffers: H2D x, one multiply, D2H y, synchronous
+            rc = self.eng.lib().smvp_csr_mult(self.A._h, ctypes.c_void_p(hx.data_ptr()), ctypes.c_void_p(hy.data_ptr()), 1,
+                                             None, self.variant)
+            if rc != 0:
+                raise self.eng.SmvpError(rc, "smvp_csr_mult")
+        else:
+            self.x.copy_(hx, non_blocking=True)
+            self.step(stream)
+            hy.copy_(self.y_local, non_blocking=True)
+            stream.synchronize()
+
+    def measured_traffic_bytes(self):
+        return _measured_traffic(self.kernel_name)
+
+    def free(self):
+        self.A.free()
+        self.y_full = self.y_local = None
+
+
+class ColBlockTjds:
+    """y = A x with A in TJDS, columns cut into nnz-balanced blocks over `world` ranks; partial y reduce-scattered."""
+
+    def __init__(self, eng, source, rank, world, variant=0, exchange="nccl"):
+        import torch
+
+        self.eng, self.rank, self.world, self.variant, self.exchange = eng, rank, world, variant, exchange
+        self.M, self.N = source.rows, source.cols
+        self.bounds = balanced_bounds(source.col_prefix, self.N, world)
+        self.c0, self.c1 = self.bounds[rank], self.bounds[rank + 1]
+        r, c, v = source.col_block(self.c0, self.c1)
+        self.local_nnz = r.n
+        self.T = eng.TjdsMatrix.build_device(r, c, v, self.M, self.c1 - self.c0, r.n)
+        for a in (r, c, v):
+            a.free()
+        if hasattr(source, "release") and world == 1:
+            source.release()
+        self.global_nnz = source.nnz
+        # ndiag of the whole matrix is the max over ranks of the local ndiag
+        nd = self.T.ndiag
+        if world > 1:
+            import torch.distributed as dist
+
+            t = torch.tensor([nd], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            nd = int(t[0])
+        self.ndiag = nd
+        self.global_bytes_per_mult = 12 * source.nnz + 4 * (nd + 1) + 8 * self.N + 8 * self.M
+        self.local_bytes_per_mult = self.T.bytes_per_mult
+        self.Mp = -(-self.M // world) * world
+        self.y_partial = torch.zeros(self.Mp, dtype=torch.float64, device="cuda")
+        self.y_owned = torch.zeros(self.Mp // world, dtype=torch.float64, device="cuda")
+        self.local_rows_out = self.Mp // world
+        self.variant_name = {eng.TJDS_ATOMIC: "atomic", eng.TJDS_DETERMINISTIC: "deterministic"}[variant]
+        self.kernel_name = "tjds_%s_kernel" % ("atomic" if variant == eng.TJDS_ATOMIC else "det")
+        self.partition_desc = ("column blocks balanced by nnz, %d ranks; x sliced; partial y %s" %
+                               (world, "reduce-scattered over NCCL" if (world > 1 and exchange == "nccl") else "kept local"))
+        self.e2e_api = ("smvp_tjds_mult(A, x_host, y_host, iters=1) [C ABI, pinned host buffers]" if world == 1 else
+                        "H2D x slice -> smvp_tjds_set_x_device + smvp_tjds_mult_device -> NCCL reduce-scatter -> D2H y block")
+        self.x = None
+
+    def set_x(self, x, stream=None):
+        self.x = x
+        self.T.set_x_device(x[self.c0:self.c1], stream)
+
+    def multiply(self, stream=None):
+        self.T.mult_device(self.y_partial, self.variant, 0, stream)
+
+    def exchange_y(self, stream=None):
+        if self.world > 1 and self.exchange == "nccl":
+            import torch.distributed as dist
+
+            dist.reduce_scatter_tensor(self.y_owned, self.y_partial, op=dist.ReduceOp.SUM)
+
+    def step(self, stream=None):
+        self.multiply(stream)
+        self.exchange_y(stream)
+
+    def e2e_step(self, hx, hy, stream):
+        import ctypes
+
+        if self.world == 1:
+            rc = self.eng.lib().smvp_tjds_mult(self.T._h, ctypes.c_void_p(hx.data_ptr()), ctypes.c_void_p(hy.data_ptr()), 1,
+                                              None, self.variant, 0)
+            if rc != 0:
+                raise self.eng.SmvpError(rc, "smvp_tjds_mult")
+        else:
+            self.x.copy_(hx, non_blocking=True)
+            self.T.set_x_device(self.x[self.c0:self.c1], stream)
+            self.step(stream)
+            hy.copy_(self.y_owned, non_blocking=True)
+            stream.synchronize()
+
+    def measured_traffic_bytes(self):
+        return _measured_traffic(self.kernel_name)
+
+    def free(self):
+        self.T.free()
+        self.y_partial = self.y_owned = None
