@@ -10,15 +10,16 @@
 //          Right for long regular rows and for matrices so small that launch latency is the cost.
 //
 //  MERGE   merge-path (Merrill & Garland): the list of row ends and the list of nonzeros are merged
-//          conceptually and cut into equal tiles of THREADS*IPT items, so no row-length skew can
-//          unbalance a CTA or a thread.  Persistent CTAs; the val / col_ind / row_end slices of a tile
-//          are staged into shared memory by the TMA engine (cp.async.bulk + mbarrier, evict-first in
-//          L2) through a multi-stage ring, so HBM streaming never waits for the math.  Each thread
-//          owns IPT consecutive merge items: it first issues all its x gathers (independent, so IPT
-//          loads are in flight per thread), then walks its items sequentially.  With IPT ~ mean row
-//          length + 1 neighbouring lanes work on neighbouring rows, which is what makes the x gather
-//          of a banded matrix (27-point stencil) coalesce.  Rows cut by a thread or tile boundary are
-//          stitched in a fixed order (no atomics): the kernel is deterministic.
+//          conceptually and cut into equal tiles of 32*IPT items, so no row-length skew can
+//          unbalance a warp or a lane.  Persistent, WARP-AUTONOMOUS: every warp owns a shared-memory
+//          stage and an mbarrier, stages the val / col_ind / row_end slices of its tile with its own
+//          TMA bulk copies (cp.async.bulk, evict-first in L2) and never meets a block-wide barrier.
+//          Each lane owns IPT consecutive merge items: it first issues all its x gathers (independent,
+//          IPT loads in flight per lane), then walks its items sequentially.  Lanes IPT items apart
+//          sit on neighbouring rows at the same stencil position, which is what makes the x gather of
+//          a banded matrix coalesce (2-3 sectors per request instead of ~22 for the vector kernel).
+//          Rows cut by a lane boundary are stitched with a segmented warp scan, rows cut by a tile
+//          boundary by a small fix-up kernel -- fixed order, no atomics: the kernel is deterministic.
 //
 // Arithmetic: products and sums are separate roundings (__dmul_rn/__dadd_rn), like the reference's
 // mulsd+addsd; a row that lies inside one thread is summed in exactly the reference's order.
@@ -226,98 +227,149 @@ __device__ __forceinline__ TileView make_tile(const int32_t *__restrict__ tile_r
     return v;
 }
 
-template <int THREADS, int IPT, int STAGES>
-__global__ void __launch_bounds__(THREADS, 1)
-    csr_merge_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_ind, const double *__restrict__ val,
-                     const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int32_t rows,
-                     int64_t nnz, int32_t num_tiles, int32_t *__restrict__ carry_row, double *__restrict__ carry_val)
+// ---------------------------------------------------------------------------------------------
+// Warp-autonomous merge-path: the unit of work is a WARP tile of 32*IPT merge items.  Every warp owns
+// its shared-memory stage(s) and its mbarrier, fetches its tiles with its own TMA bulk copies and
+// never meets a block-wide barrier: warps of a CTA drift apart freely, so while one waits for HBM
+// or for its x gathers the others walk.  Rows cut by lane boundaries are stitched with a segmented
+// warp scan (__shfl_up_sync), rows cut by tile boundaries by the fix-up kernel -- fixed order, no atomics.
+template <int WARPS, int IPT, int STAGES, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+    csr_merge_warp_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_ind, const double *__restrict__ val,
+                          const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int32_t rows,
+                          int64_t nnz, int32_t num_tiles, int32_t *__restrict__ carry_row, double *__restrict__ carry_val)
 {
-    using Shape = MergeShape<THREADS, IPT, STAGES>;
+    using Shape = MergeShape<32, IPT, STAGES>;
     extern __shared__ __align__(128) unsigned char stage_mem[];
-    __shared__ __align__(8) uint64_t full_bar[STAGES];
-    __shared__ int32_t s_j[THREADS + 1];
-    __shared__ double s_carry[THREADS];
+    __shared__ __align__(8) uint64_t full_bar[WARPS * STAGES];
 
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t total = (int64_t)rows + nnz;
+    unsigned char *my_stages = stage_mem + (size_t)w * Shape::SMEM_BYTES;
+    uint64_t *my_bar = &full_bar[w * STAGES];
     uint64_t policy = 0;
-
-    if (tid == 0)
+    if (lane == 0)
     {
 #pragma unroll
         for (int s = 0; s < STAGES; s++)
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&my_bar[s], 1);
         fence_mbar_init();
         policy = l2_evict_first_policy();
     }
-    __syncthreads();
+    __syncwarp();
 
-    auto issue = [&](int32_t t, int s) {
-        const TileView v = make_tile(tile_row, t, Shape::TILE, total);
-        unsigned char *base = stage_mem + (size_t)s * Shape::STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], v.vb + v.cb + v.rb);
+    const int64_t warp_stride = (int64_t)gridDim.x * WARPS;
+    const int64_t first_tile = (int64_t)blockIdx.x * WARPS + w;
+
+    auto issue = [&](const TileView &v, int s) { // lane 0 only
+        unsigned char *base = my_stages + (size_t)s * Shape::STAGE_BYTES;
+        mbar_expect_tx(&my_bar[s], v.vb + v.cb + v.rb);
         if (v.vb)
-            bulk_g2s(base, val + v.va, v.vb, &full_bar[s], policy);
+            bulk_g2s(base, val + v.va, v.vb, &my_bar[s], policy);
         if (v.cb)
-            bulk_g2s(base + v.vb, col_ind + v.ca, v.cb, &full_bar[s], policy);
+            bulk_g2s(base + v.vb, col_ind + v.ca, v.cb, &my_bar[s], policy);
         if (v.rb)
-            bulk_g2s(base + v.vb + v.cb, row_ptr + v.ra, v.rb, &full_bar[s], policy);
+            bulk_g2s(base + v.vb + v.cb, row_ptr + v.ra, v.rb, &my_bar[s], policy);
     };
 
-    if (tid == 0)
-    {
+    // prologue: fill the ring
+    TileView ring[STAGES];
 #pragma unroll
-        for (int s = 0; s < STAGES; s++)
+    for (int s = 0; s < STAGES; s++)
+    {
+        const int64_t t = first_tile + (int64_t)s * warp_stride;
+        if (t < num_tiles)
         {
-            const int64_t t = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
-            if (t < num_tiles)
-                issue((int32_t)t, s);
+            ring[s] = make_tile(tile_row, (int32_t)t, Shape::TILE, total);
+            if (lane == 0)
+                issue(ring[s], s);
         }
     }
 
     int k = 0;
-    for (int64_t t64 = blockIdx.x; t64 < num_tiles; t64 += gridDim.x, k++)
+    for (int64_t t64 = first_tile; t64 < num_tiles; t64 += warp_stride, k++)
     {
-        const int32_t t = (int32_t)t64;
         const int s = k % STAGES;
         const uint32_t parity = (uint32_t)(k / STAGES) & 1u;
-        const TileView v = make_tile(tile_row, t, Shape::TILE, total);
-        unsigned char *base = stage_mem + (size_t)s * Shape::STAGE_BYTES;
-        const double *sval = reinterpret_cast<const double *>(base) - v.va;                  // index by global nnz
-        const int32_t *scol = reinterpret_cast<const int32_t *>(base + v.vb) - v.ca;          // index by global nnz
-        const int32_t *srow = reinterpret_cast<const int32_t *>(base + v.vb + v.cb) - v.ra;   // index by row_ptr slot
-        // row_end of tile-local row i, relative to the tile's first nonzero
+        TileView v;
+#pragma unroll
+        for (int q = 0; q < STAGES; q++) // static indexing keeps the ring in registers
+            if (q == s)
+                v = ring[q];
+        unsigned char *base = my_stages + (size_t)s * Shape::STAGE_BYTES;
+        const double *sval = reinterpret_cast<const double *>(base) - v.va;
+        const int32_t *scol = reinterpret_cast<const int32_t *>(base + v.vb) - v.ca;
+        const int32_t *srow = reinterpret_cast<const int32_t *>(base + v.vb + v.cb) - v.ra;
         auto row_end = [&](int32_t i) -> int32_t { return srow[v.r0 + 1 + i] - (int32_t)v.n0; };
 
-        mbar_wait(&full_bar[s], parity);
+        mbar_wait(&my_bar[s], parity);
 
-        // ---- where do my IPT items start?  (merge-path search inside the tile)
-        int32_t d = tid * IPT;
+        // ---- my first merge item: interpolate, gallop, bisect (2 probes on regular matrices)
+        int32_t d = lane * IPT;
         if (d > v.items_t)
             d = v.items_t;
         int32_t lo = d > v.nnz_t ? d - v.nnz_t : 0, hi = d < v.rows_t ? d : v.rows_t;
-        while (lo < hi)
+        if (lo < hi)
         {
-            const int32_t mid = (lo + hi) >> 1;
-            if (row_end(mid) <= d - mid - 1)
-                lo = mid + 1;
+            int32_t g = (int32_t)(((int64_t)d * v.rows_t) / v.items_t);
+            g = g < lo ? lo : (g > hi - 1 ? hi - 1 : g);
+            int32_t step = 1;
+            if (row_end(g) <= d - g - 1)
+            {
+                lo = g + 1;
+                while (lo < hi)
+                {
+                    const int32_t m = (lo + step - 1 < hi - 1) ? lo + step - 1 : hi - 1;
+                    if (row_end(m) <= d - m - 1)
+                    {
+                        lo = m + 1;
+                        step <<= 1;
+                    }
+                    else
+                    {
+                        hi = m;
+                        break;
+                    }
+                }
+            }
             else
-                hi = mid;
+            {
+                hi = g;
+                while (lo < hi)
+                {
+                    const int32_t m = (hi - step > lo) ? hi - step : lo;
+                    if (!(row_end(m) <= d - m - 1))
+                    {
+                        hi = m;
+                        step <<= 1;
+                    }
+                    else
+                    {
+                        lo = m + 1;
+                        break;
+                    }
+                }
+            }
+            while (lo < hi)
+            {
+                const int32_t mid = (lo + hi) >> 1;
+                if (row_end(mid) <= d - mid - 1)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
         }
-        const int32_t i0 = lo;      // my first row (tile-local)
-        const int32_t j0 = d - lo;  // my first nonzero (tile-local)
-        s_j[tid] = j0;
-        if (tid == 0)
-            s_j[THREADS] = v.nnz_t;
-        __syncthreads();
-        int32_t d_next = (tid + 1) * IPT;
+        const int32_t i0 = lo, j0 = d - lo;
+        int32_t d_next = (lane + 1) * IPT;
         if (d_next > v.items_t)
             d_next = v.items_t;
-        const int32_t j_next = s_j[tid + 1];
+        int32_t j_next = __shfl_down_sync(0xffffffffu, j0, 1);
+        if (lane == 31)
+            j_next = v.nnz_t;
         const int32_t i_next = d_next - j_next;
         const int32_t cnt = j_next - j0;
 
-        // ---- all my gathers first: IPT independent loads in flight
+        // ---- all my gathers first
         double prod[IPT];
         {
             const int64_t jg = v.n0 + j0;
@@ -372,49 +424,46 @@ __global__ void __launch_bounds__(THREADS, 1)
             sum = 0.0;
             row++;
         }
-        s_carry[tid] = sum; // partial of row i_next, continued by the next thread
-        __syncthreads();
 
-        // ---- stitch rows cut by thread boundaries, in ascending thread order (deterministic)
-        auto start_row = [&](int tt) -> int32_t {
-            int32_t dd = tt * IPT;
-            if (dd > v.items_t)
-                dd = v.items_t;
-            return dd - s_j[tt];
-        };
+        // ---- this stage is consumed: refill it (lane 0) while the warp stitches
+        __syncwarp();
+        {
+            const int64_t tn = t64 + (int64_t)STAGES * warp_stride;
+            if (tn < num_tiles)
+            {
+                const TileView nv = make_tile(tile_row, (int32_t)tn, Shape::TILE, total);
+#pragma unroll
+                for (int q = 0; q < STAGES; q++)
+                    if (q == s)
+                        ring[q] = nv;
+                if (lane == 0)
+                    issue(nv, s);
+            }
+        }
+
+        // ---- stitch rows cut by lane boundaries: segmented inclusive scan of (carry row, carry sum)
+        const int32_t key = i_next; // the row my trailing partial belongs to
+        double scan = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const double pv = __shfl_up_sync(0xffffffffu, scan, o);
+            const int32_t pk = __shfl_up_sync(0xffffffffu, key, o);
+            if (lane >= o && pk == key)
+                scan = __dadd_rn(pv, scan);
+        }
+        const double prev_scan = __shfl_up_sync(0xffffffffu, scan, 1);
+        const int32_t prev_key = __shfl_up_sync(0xffffffffu, key, 1);
         if (has_first)
         {
-            double acc = first_sum;
-            if (tid > 0)
-            {
-                int tl = tid - 1;
-                while (tl >= 1 && start_row(tl) == i0)
-                    tl--;
-                acc = s_carry[tl];
-                for (int tt = tl + 1; tt < tid; tt++)
-                    acc = __dadd_rn(acc, s_carry[tt]);
-                acc = __dadd_rn(acc, first_sum);
-            }
-            yt[i0] = acc;
+            if (lane > 0 && prev_key == i0)
+                first_sum = __dadd_rn(prev_scan, first_sum);
+            yt[i0] = first_sum;
         }
-        if (tid == THREADS - 1)
+        if (lane == 31)
         {
-            int tl = THREADS - 1;
-            while (tl >= 1 && start_row(tl) == v.rows_t)
-                tl--;
-            double acc = s_carry[tl];
-            for (int tt = tl + 1; tt < THREADS; tt++)
-                acc = __dadd_rn(acc, s_carry[tt]);
-            carry_row[t] = v.r0 + v.rows_t;
-            carry_val[t] = acc;
-        }
-        __syncthreads(); // stage s, s_j and s_carry are free again
-
-        if (tid == 0)
-        {
-            const int64_t tn = t64 + (int64_t)STAGES * gridDim.x;
-            if (tn < num_tiles)
-                issue((int32_t)tn, s);
+            carry_row[(int32_t)t64] = v.r0 + v.rows_t;
+            carry_val[(int32_t)t64] = scan;
         }
     }
 }
@@ -436,34 +485,32 @@ __global__ void __launch_bounds__(256) merge_fixup_kernel(const int32_t *__restr
     y[r] = __dadd_rn(acc, y[r]);
 }
 
-// ---- the instantiations AUTO chooses from
-struct MergeCfg
-{
-    int threads, ipt, stages;
-};
-static const MergeCfg kMergeCfgs[] = {
-    {256, 12, 4}, // 0: short rows (mean < ~14)
-    {256, 20, 3}, // 1: mean ~ 14..22
-    {256, 28, 2}, // 2: mean ~ 23+  (27-point stencil: one row per thread)
-};
-constexpr int kNumMergeCfgs = sizeof(kMergeCfgs) / sizeof(kMergeCfgs[0]);
+// ---- the instantiations AUTO chooses from: {warps per CTA, items per thread, stages per warp, min CTAs/SM}.
+// Measured on B200 (tools/sweep_csr.py; logs under profiles/): shared memory holds 12 B per staged
+// nonzero, so the items per thread bound how many warps an SM can keep busy; single-stage warps at
+// <= 64 registers (32 warps/SM) beat deeper rings, and any register spill halves the throughput.
+static int wmerge_tile_items(int cfg);
 
 static int pick_merge_cfg(const smvp_csr *A)
 {
     const char *env = getenv("SMVP_MERGE_CFG");
-    if (env && env[0] >= '0' && env[0] < '0' + kNumMergeCfgs)
-        return env[0] - '0';
+    if (env && env[0])
+    {
+        const int v = atoi(env);
+        if (wmerge_tile_items(v) > 0)
+            return v;
+    }
     const double mean = A->rows > 0 ? (double)A->nnz / A->rows : 0.0;
-    if (mean < 14.0)
-        return 0;
-    if (mean < 22.5)
-        return 1;
-    return 2;
+    const bool skewed = A->max_row_nnz > 64.0 * (mean + 1.0);
+    if (skewed || mean < 20.0)
+        return 1; // 10 items per thread
+    return 0;     // 14 items per thread: two lanes per 27-point-stencil row
 }
 
 static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
 {
-    if (A->merge_cfg == cfg)
+    const int32_t tile_items = wmerge_tile_items(cfg);
+    if (A->merge_cfg == tile_items)
         return SMVP_OK;
     cudaFree(A->tile_row);
     cudaFree(A->carry_row);
@@ -471,7 +518,6 @@ static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
     A->tile_row = A->carry_row = nullptr;
     A->carry_val = nullptr;
     A->merge_cfg = -1;
-    const int32_t tile_items = kMergeCfgs[cfg].threads * kMergeCfgs[cfg].ipt;
     const int64_t total = (int64_t)A->rows + A->nnz;
     const int64_t tiles = ceil_div64(total, tile_items);
     if (tiles > 0x7ffffff0LL)
@@ -483,34 +529,64 @@ static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
     SMVP_LAUNCH(merge_plan_kernel, (unsigned)ceil_div64(tiles + 1, 256), 256, 0, s, A->row_ptr, A->rows, A->nnz, tile_items,
                 (int32_t)tiles, A->tile_row);
     SMVP_CUDA(cudaGetLastError());
-    A->merge_cfg = cfg;
+    A->merge_cfg = tile_items; // the plan depends on the tile size only
     return SMVP_OK;
 }
 
-template <int THREADS, int IPT, int STAGES>
-static int launch_merge(const smvp_csr *A, const double *d_x, double *d_y, cudaStream_t s)
+#define SMVP_WMERGE_CFGS(X) \
+    X(0, 2, 14, 1, 16)      \
+    X(1, 2, 10, 1, 16)      \
+    X(2, 4, 14, 1, 8)       \
+    X(3, 4, 28, 1, 5)       \
+    X(4, 2, 28, 1, 10)      \
+    X(5, 4, 7, 1, 12)       \
+    X(6, 2, 12, 1, 16)      \
+    X(7, 8, 14, 1, 4)
+
+template <int WARPS, int IPT, int STAGES, int MINB>
+static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, cudaStream_t s)
 {
-    using Shape = MergeShape<THREADS, IPT, STAGES>;
-    auto kern = csr_merge_kernel<THREADS, IPT, STAGES>;
+    using Shape = MergeShape<32, IPT, STAGES>;
+    constexpr int SMEM = WARPS * Shape::SMEM_BYTES;
+    auto kern = csr_merge_warp_kernel<WARPS, IPT, STAGES, MINB>;
     static thread_local int configured_dev = -1;
+    static thread_local int resident = 1;
     int dev = 0;
     SMVP_CUDA(cudaGetDevice(&dev));
     if (configured_dev != dev)
     {
-        SMVP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Shape::SMEM_BYTES));
+        SMVP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        SMVP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, WARPS * 32, SMEM));
+        if (resident < 1)
+            resident = 1;
         configured_dev = dev;
     }
-    int grid = device_props().sms;
-    if (grid > A->merge_tiles)
-        grid = A->merge_tiles;
+    int64_t grid = (int64_t)device_props().sms * resident;
+    const int64_t need = ceil_div64(A->merge_tiles, WARPS);
+    if (grid > need)
+        grid = need;
     if (grid > 0)
     {
-        SMVP_LAUNCH(kern, grid, THREADS, Shape::SMEM_BYTES, s, A->row_ptr, A->col_ind, A->val, d_x, d_y, A->tile_row, A->rows,
+        SMVP_LAUNCH(kern, (unsigned)grid, WARPS * 32, SMEM, s, A->row_ptr, A->col_ind, A->val, d_x, d_y, A->tile_row, A->rows,
                     A->nnz, A->merge_tiles, A->carry_row, A->carry_val);
         SMVP_LAUNCH(merge_fixup_kernel, (unsigned)ceil_div64(A->merge_tiles, 256), 256, 0, s, A->carry_row, A->carry_val,
                     A->merge_tiles, A->rows, d_y);
     }
     return SMVP_OK;
+}
+
+static int wmerge_tile_items(int cfg)
+{
+    switch (cfg)
+    {
+#define X(id, wp, i, st, mb) \
+    case id:                 \
+        return 32 * i;
+        SMVP_WMERGE_CFGS(X)
+#undef X
+    default:
+        return 0;
+    }
 }
 
 static int csr_mult_merge(smvp_csr *A, const double *d_x, double *d_y, cudaStream_t s)
@@ -519,12 +595,13 @@ static int csr_mult_merge(smvp_csr *A, const double *d_x, double *d_y, cudaStrea
     SMVP_TRY(merge_plan(A, cfg, s));
     switch (cfg)
     {
-    case 0:
-        return launch_merge<256, 12, 4>(A, d_x, d_y, s);
-    case 1:
-        return launch_merge<256, 20, 3>(A, d_x, d_y, s);
+#define X(id, wp, i, st, mb) \
+    case id:                 \
+        return launch_wmerge<wp, i, st, mb>(A, d_x, d_y, s);
+        SMVP_WMERGE_CFGS(X)
+#undef X
     default:
-        return launch_merge<256, 28, 2>(A, d_x, d_y, s);
+        return SMVP_E_ARG;
     }
 }
 

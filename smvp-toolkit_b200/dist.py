@@ -156,7 +156,7 @@ class RowBlockCsr:
         self.local_rows_out = self.r1 - self.r0
         resolved = self.A.auto_variant if variant == eng.CSR_AUTO else variant
         self.variant_name = {eng.CSR_VECTOR: "vector", eng.CSR_MERGE: "merge"}[resolved]
-        self.kernel_name = "csr_%s_kernel" % self.variant_name
+        self.kernel_name = {"vector": "csr_vector_kernel", "merge": "csr_merge_warp_kernel"}[self.variant_name]
         self.partition_desc = ("row blocks balanced by nnz, %d ranks; x replicated; y %s" %
                                (world, "all-gathered over NCCL" if (world > 1 and exchange == "nccl") else "kept local"))
         self.e2e_api = ("smvp_csr_mult(A, x_host, y_host, iters=1) [C ABI, pinned host buffers]" if world == 1 else
