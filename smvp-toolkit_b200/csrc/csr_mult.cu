@@ -539,9 +539,8 @@ static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
     X(2, 4, 14, 1, 8)       \
     X(3, 4, 28, 1, 5)       \
     X(4, 2, 28, 1, 10)      \
-    X(5, 4, 7, 1, 12)       \
-    X(6, 2, 12, 1, 16)      \
-    X(7, 8, 14, 1, 4)
+    X(5, 2, 12, 1, 16)      \
+    X(6, 2, 10, 1, 14)
 
 template <int WARPS, int IPT, int STAGES, int MINB>
 static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, cudaStream_t s)

@@ -56,6 +56,21 @@ def test_library_is_sm100a_with_tma(eng):
     assert "SYNCS" in sass   # mbarrier
 
 
+def test_hot_kernels_do_not_spill(eng):
+    """A register spill in the multiply kernels halves their throughput (measured, profiles/): the build must
+    stay spill-free (STACK:0) for every CSR / TJDS multiply kernel."""
+    out = subprocess.run(["cuobjdump", "-res-usage", eng.LIB_PATH], capture_output=True, text=True).stdout
+    lines = out.splitlines()
+    seen = 0
+    for i, ln in enumerate(lines):
+        if "Function" in ln and re.search(r"csr_merge_warp_kernel|csr_vector_kernel|tjds_atomic_kernel|tjds_det_kernel", ln):
+            usage = lines[i + 1]
+            m = re.search(r"STACK:(\d+)", usage)
+            assert m and int(m.group(1)) == 0, (ln, usage)
+            seen += 1
+    assert seen >= 4
+
+
 def test_no_gpu_means_loud_failure_not_fallback(eng):
     import torch
 

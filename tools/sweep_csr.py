@@ -45,7 +45,9 @@ def main():
     ap.add_argument("--edge-factor", type=int, default=16)
     ap.add_argument("--cfgs", default="0-11")
     ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--grid-modes", default="persistent,tiles")
+    ap.add_argument("--grid-modes", default="persistent")
+    ap.add_argument("--chunks", default="8")
+    ap.add_argument("--aligned", default="auto", help="comma list of 0,1,auto")
     args = ap.parse_args()
     if args.workload == "stencil27":
         src = sdist.StencilSource(eng, args.grid, args.grid, args.grid)
@@ -61,18 +63,21 @@ def main():
     ms = timeit(lambda: op.A.mult_device(x, op.y_local, eng.CSR_VECTOR), args.steps)
     y_vec = op.y_local.clone()
     print("vector            : %8.3f ms  %8.1f GB/s" % (ms, nbytes / ms / 1e6), flush=True)
-    for mode in args.grid_modes.split(","):
-        os.environ["SMVP_MERGE_GRID"] = "tiles" if mode == "tiles" else ""
+    modes = [(c, a) for a in args.aligned.split(",") for c in args.chunks.split(",")]
+    for chunk, al in modes:
+        os.environ["SMVP_MERGE_CHUNK"] = chunk
+        os.environ["SMVP_MERGE_ALIGNED"] = "" if al == "auto" else al
+        mode = "chunk=%s al=%s" % (chunk, al)
         for cfg in parse_list(args.cfgs):
             os.environ["SMVP_MERGE_CFG"] = str(cfg)
             op.y_local.fill_(float("nan"))
             try:
                 ms = timeit(lambda: op.A.mult_device(x, op.y_local, eng.CSR_MERGE), args.steps)
             except Exception as e:  # noqa: BLE001
-                print("merge cfg %2d %-10s: FAILED %s" % (cfg, mode, e), flush=True)
+                print("merge cfg %2d %-16s: FAILED %s" % (cfg, mode, e), flush=True)
                 continue
             err = float(torch.linalg.norm(op.y_local - y_vec) / torch.linalg.norm(y_vec))
-            print("merge cfg %2d %-10s: %8.3f ms  %8.1f GB/s  rel_l2_vs_vector=%.2e" % (cfg, mode, ms, nbytes / ms / 1e6, err), flush=True)
+            print("merge cfg %2d %-16s: %8.3f ms  %8.1f GB/s  rel_l2_vs_vector=%.2e" % (cfg, mode, ms, nbytes / ms / 1e6, err), flush=True)
 
 
 if __name__ == "__main__":
