@@ -44,7 +44,7 @@ def parse_args():
     p.add_argument("--edge-factor", type=int, default=16)
     p.add_argument("--format", default="csr", choices=["csr", "tjds"])
     p.add_argument("--variant", default="auto", choices=["auto", "vector", "merge", "atomic", "deterministic"])
-    p.add_argument("--exchange", default="nccl", choices=["nccl", "none"],
+    p.add_argument("--exchange", default="auto", choices=["auto", "multicast", "p2p", "nccl", "none"],
                    help="N>1: collective after the multiply (allgather of y for CSR, reduce-scatter for TJDS)")
     p.add_argument("--cpu-grid", type=int, default=100, help="grid edge of the bounded CPU sample (stencil27)")
     p.add_argument("--cpu-scale", type=int, default=20, help="scale of the bounded CPU sample (rmat)")
@@ -202,7 +202,7 @@ def run_reference_arm(args):
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.time() - t0,
     }
-    print(json.dumps(line), flush=True)
+    print_json(line)
 
 
 def workload_config(args, extra):
@@ -268,12 +268,32 @@ def run_ours(args):
     else:
         M = N = 1 << args.scale
         gen = sdist.RmatSource(eng, args.scale, args.edge_factor << args.scale)
+    exch = "none" if world == 1 else args.exchange
     if args.format == "csr":
-        op = sdist.RowBlockCsr(eng, gen, rank, world, variant_map.get(args.variant, eng.CSR_AUTO),
-                               exchange=args.exchange if world > 1 else "none")
+        # "auto": the fused paths first (measured on B200, profiles/: in-kernel multicast stores beat in-kernel
+        # unicast fan-out, both beat SpMV followed by an NCCL allgather), NCCL as the fallback of last resort
+        candidates = ["multicast", "p2p", "nccl"] if exch == "auto" else [exch]
+        op, err = None, None
+        for cand in candidates:
+            try:
+                op = sdist.RowBlockCsr(eng, gen, rank, world, variant_map.get(args.variant, eng.CSR_AUTO), exchange=cand,
+                                       release_source=(cand == candidates[-1]))
+            except Exception as e:  # noqa: BLE001  (e.g. no NVSwitch multicast on this box)
+                op, err = None, e
+            if world > 1:
+                ok = torch.tensor([1 if op is not None else 0], device="cuda")
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok[0]) == 0 and op is not None:
+                    op.free()
+                    op = None
+            if op is not None:
+                exch = cand
+                break
+        if op is None:
+            raise err if err is not None else RuntimeError("no exchange could be set up on every rank")
     else:
         op = sdist.ColBlockTjds(eng, gen, rank, world, tj_map.get(args.variant, eng.TJDS_ATOMIC),
-                                exchange=args.exchange if world > 1 else "none")
+                                exchange="nccl" if exch in ("multicast", "p2p", "nccl") else "none", release_source=True)
     torch.cuda.synchronize()
     build_s = time.time() - t_build0
     nnz_total = op.global_nnz
@@ -374,7 +394,7 @@ def run_ours(args):
             res = cpu_reference_run(args, args.cpu_iters)
             line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": 1, "kind": res["kind"],
                                     "sample": res["sample"], "gflops": res["gflops"]}
-        print(json.dumps(line), flush=True)
+        print_json(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -382,6 +402,15 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version there) are
+    # sent to stderr, and the line is written to the real stdout at the end
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global print_json
+
+    def print_json(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     if args.impl == "reference":
         run_reference_arm(args)
     else:

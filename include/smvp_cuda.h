@@ -105,6 +105,12 @@ int smvp_tjds_build_device(const int32_t *d_row, const int32_t *d_col, const dou
                            int32_t cols, int64_t nnz, smvp_tjds **out); /* synchronous */
 /* one pass y = A x */
 int smvp_csr_mult_device(smvp_csr *A, const double *d_x, double *d_y, int variant, void *stream);
+/* one pass y = A x with the result stored into n_out (<= 8) destinations at once: d_y_list[k][r] = y[r] for
+ * every row r of A and every k.  The destinations may be peer-mapped buffers of other GPUs (NVLink symmetric
+ * memory): this is how the row-partitioned multi-GPU path fuses the "allgather of y" into the SpMV epilogue.
+ * d_y_list is a HOST array of device pointers; the destinations are write-only for the library.             */
+int smvp_csr_mult_device_fanout(smvp_csr *A, const double *d_x, double *const *d_y_list, int n_out, int variant,
+                                void *stream);
 /* x_perm[p] = x[perm[p]] into the handle (the reference permutes x once, at build time, main-cli.c:907-923) */
 int smvp_tjds_set_x_device(smvp_tjds *A, const double *d_x, void *stream);
 /* one pass y = A x with the x last given to smvp_tjds_set_x_device; zero-fills y first */

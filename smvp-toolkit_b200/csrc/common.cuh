@@ -118,8 +118,8 @@ struct smvp_csr
     int32_t merge_cfg;      // which template instantiation the plan was made for (-1 none)
     int32_t merge_tiles;
     int32_t *tile_row;      // [merge_tiles+1] rows consumed before each tile
-    int32_t *carry_row;     // [merge_tiles]
-    double *carry_val;      // [merge_tiles]
+    double *head_val;       // [merge_tiles] partial of the first row that ends in the tile
+    double *carry_val;      // [merge_tiles] partial of the row that continues past the tile
     // scratch for the host-vector entry point
     double *d_x, *d_y;
 };

@@ -33,7 +33,7 @@ static void csr_release(smvp_csr *A)
     cudaFree(A->col_ind);
     cudaFree(A->val);
     cudaFree(A->tile_row);
-    cudaFree(A->carry_row);
+    cudaFree(A->head_val);
     cudaFree(A->carry_val);
     cudaFree(A->d_x);
     cudaFree(A->d_y);

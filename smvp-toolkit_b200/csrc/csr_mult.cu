@@ -81,11 +81,34 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                  : "memory");
 }
 
+// ------------------------------------------------------------------ where y goes
+// Single GPU: one pointer.  Multi GPU (row blocks): every rank must end with the whole y, so
+// the multiply kernels store each finished row straight into every peer's copy of y over NVLink
+// (peer-mapped symmetric memory): the "allgather" is fused into the SpMV epilogue and overlaps the
+// streaming of the matrix instead of following it.  y is only ever written, never read.
+constexpr int SMVP_MAX_FANOUT = 8;
+struct YFan
+{
+    double *p[SMVP_MAX_FANOUT];
+    int n;
+};
+template <bool FANOUT>
+__device__ __forceinline__ void store_y(double *__restrict__ y, const YFan &fan, int64_t row, double v)
+{
+    if (FANOUT)
+    {
+        for (int k = 0; k < fan.n; k++)
+            fan.p[k][row] = v;
+    }
+    else
+        y[row] = v;
+}
+
 // =====================================================================================  VECTOR
-template <int LPR>
+template <int LPR, bool FANOUT>
 __global__ void __launch_bounds__(256) csr_vector_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_ind,
                                                          const double *__restrict__ val, const double *__restrict__ x,
-                                                         double *__restrict__ y, int32_t rows)
+                                                         double *__restrict__ y, int32_t rows, const __grid_constant__ YFan fan)
 {
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t row = gt / LPR;
@@ -124,35 +147,42 @@ __global__ void __launch_bounds__(256) csr_vector_kernel(const int32_t *__restri
     for (int o = LPR / 2; o > 0; o >>= 1)
         sum = __dadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
     if (row < rows && lane == 0)
-        y[row] = sum;
+        store_y<FANOUT>(y, fan, row, sum);
 }
 
 template <int LPR>
-static int launch_vector(const smvp_csr *A, const double *d_x, double *d_y, cudaStream_t s)
+static int launch_vector(const smvp_csr *A, const double *d_x, double *d_y, const YFan *fan, cudaStream_t s)
 {
     const int64_t threads = (int64_t)A->rows * LPR;
     const int64_t blocks = ceil_div64(threads, 256);
     if (blocks > 0x7fffffffLL)
         return SMVP_E_TOOBIG;
     if (blocks > 0)
-        SMVP_LAUNCH(csr_vector_kernel<LPR>, (unsigned)blocks, 256, 0, s, A->row_ptr, A->col_ind, A->val, d_x, d_y, A->rows);
+    {
+        if (fan)
+            SMVP_LAUNCH((csr_vector_kernel<LPR, true>), (unsigned)blocks, 256, 0, s, A->row_ptr, A->col_ind, A->val, d_x, d_y,
+                        A->rows, *fan);
+        else
+            SMVP_LAUNCH((csr_vector_kernel<LPR, false>), (unsigned)blocks, 256, 0, s, A->row_ptr, A->col_ind, A->val, d_x, d_y,
+                        A->rows, YFan());
+    }
     return SMVP_OK;
 }
 
-static int csr_mult_vector(const smvp_csr *A, const double *d_x, double *d_y, cudaStream_t s)
+static int csr_mult_vector(const smvp_csr *A, const double *d_x, double *d_y, const YFan *fan, cudaStream_t s)
 {
     const double mean = A->rows > 0 ? (double)A->nnz / A->rows : 0.0;
     int rc;
     if (mean <= 8.0)
-        rc = launch_vector<2>(A, d_x, d_y, s);
+        rc = launch_vector<2>(A, d_x, d_y, fan, s);
     else if (mean <= 16.0)
-        rc = launch_vector<4>(A, d_x, d_y, s);
+        rc = launch_vector<4>(A, d_x, d_y, fan, s);
     else if (mean <= 32.0)
-        rc = launch_vector<8>(A, d_x, d_y, s);
+        rc = launch_vector<8>(A, d_x, d_y, fan, s);
     else if (mean <= 64.0)
-        rc = launch_vector<16>(A, d_x, d_y, s);
+        rc = launch_vector<16>(A, d_x, d_y, fan, s);
     else
-        rc = launch_vector<32>(A, d_x, d_y, s);
+        rc = launch_vector<32>(A, d_x, d_y, fan, s);
     return rc;
 }
 
@@ -233,11 +263,11 @@ __device__ __forceinline__ TileView make_tile(const int32_t *__restrict__ tile_r
 // never meets a block-wide barrier: warps of a CTA drift apart freely, so while one waits for HBM
 // or for its x gathers the others walk.  Rows cut by lane boundaries are stitched with a segmented
 // warp scan (__shfl_up_sync), rows cut by tile boundaries by the fix-up kernel -- fixed order, no atomics.
-template <int WARPS, int IPT, int STAGES, int MINB>
+template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     csr_merge_warp_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_ind, const double *__restrict__ val,
                           const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int32_t rows,
-                          int64_t nnz, int32_t num_tiles, int32_t *__restrict__ carry_row, double *__restrict__ carry_val)
+                          int64_t nnz, int32_t num_tiles, double *__restrict__ head_val, double *__restrict__ carry_val, const __grid_constant__ YFan fan)
 {
     using Shape = MergeShape<32, IPT, STAGES>;
     extern __shared__ __align__(128) unsigned char stage_mem[];
@@ -390,7 +420,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         bool has_first = false;
         int32_t row = i0;
         int32_t end = row < v.rows_t ? row_end(row) : 0x7fffffff;
-        double *yt = y + v.r0;
 #pragma unroll
         for (int q = 0; q < IPT; q++)
         {
@@ -404,7 +433,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                         first_sum = sum;
                     }
                     else
-                        yt[row] = sum;
+                        store_y<FANOUT>(y, fan, (int64_t)v.r0 + row, sum);
                     sum = 0.0;
                     row++;
                     end = row < v.rows_t ? row_end(row) : 0x7fffffff;
@@ -420,7 +449,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                 first_sum = sum;
             }
             else
-                yt[row] = sum;
+                store_y<FANOUT>(y, fan, (int64_t)v.r0 + row, sum);
             sum = 0.0;
             row++;
         }
@@ -458,31 +487,46 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         {
             if (lane > 0 && prev_key == i0)
                 first_sum = __dadd_rn(prev_scan, first_sum);
-            yt[i0] = first_sum;
+            // the tile's first row may have started in earlier tiles: its partial goes to the fix-up
+            // kernel, which adds the carries and writes y.  y itself is only ever WRITTEN here (never
+            // read), so it may be a write-only mapping such as an NVSwitch multicast address.
+            if (i0 == 0)
+                head_val[(int32_t)t64] = first_sum;
+            else
+                store_y<FANOUT>(y, fan, (int64_t)v.r0 + i0, first_sum);
         }
         if (lane == 31)
-        {
-            carry_row[(int32_t)t64] = v.r0 + v.rows_t;
-            carry_val[(int32_t)t64] = scan;
-        }
+            carry_val[(int32_t)t64] = scan; // partial of the row that continues into the next tile
     }
 }
 
-// rows cut by TILE boundaries: y[row] already holds the partial of the tile where the row ends;
-// add the carries of the tiles before it, in tile order.
-__global__ void __launch_bounds__(256) merge_fixup_kernel(const int32_t *__restrict__ carry_row, const double *__restrict__ carry_val,
-                                                          int32_t num_tiles, int32_t rows, double *__restrict__ y)
+// First row of every tile that ends a row there: y[row] = (carries of the tiles the row crossed, in tile
+// order) + (partial of the tile where it ends).  tile_row[u+1] is the row tile u's carry belongs to.
+template <bool FANOUT>
+__global__ void __launch_bounds__(256) merge_fixup_kernel(const int32_t *__restrict__ tile_row, const double *__restrict__ head_val,
+                                                          const double *__restrict__ carry_val, int32_t num_tiles,
+                                                          double *__restrict__ y, const __grid_constant__ YFan fan)
 {
     const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= num_tiles)
         return;
-    const int32_t r = carry_row[t];
-    if (r >= rows || (t > 0 && carry_row[t - 1] == r))
-        return;
-    double acc = carry_val[t];
-    for (int32_t u = t + 1; u < num_tiles && carry_row[u] == r; u++)
-        acc = __dadd_rn(acc, carry_val[u]);
-    y[r] = __dadd_rn(acc, y[r]);
+    const int32_t r = tile_row[t];
+    if (tile_row[t + 1] == r)
+        return; // no row ends in this tile
+    int32_t u = t; // carries of tiles [u, t-1] belong to row r
+    while (u > 0 && tile_row[u] == r)
+        u--;
+    if (tile_row[u + 1] != r)
+        u++;
+    double acc = head_val[t];
+    if (u < t)
+    {
+        acc = carry_val[u];
+        for (int32_t k = u + 1; k < t; k++)
+            acc = __dadd_rn(acc, carry_val[k]);
+        acc = __dadd_rn(acc, head_val[t]);
+    }
+    store_y<FANOUT>(y, fan, r, acc);
 }
 
 // ---- the instantiations AUTO chooses from: {warps per CTA, items per thread, stages per warp, min CTAs/SM}.
@@ -513,10 +557,10 @@ static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
     if (A->merge_cfg == tile_items)
         return SMVP_OK;
     cudaFree(A->tile_row);
-    cudaFree(A->carry_row);
+    cudaFree(A->head_val);
     cudaFree(A->carry_val);
-    A->tile_row = A->carry_row = nullptr;
-    A->carry_val = nullptr;
+    A->tile_row = nullptr;
+    A->head_val = A->carry_val = nullptr;
     A->merge_cfg = -1;
     const int64_t total = (int64_t)A->rows + A->nnz;
     const int64_t tiles = ceil_div64(total, tile_items);
@@ -524,7 +568,7 @@ static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
         return SMVP_E_TOOBIG;
     A->merge_tiles = (int32_t)tiles;
     SMVP_CUDA(dev_alloc(&A->tile_row, tiles + 1));
-    SMVP_CUDA(dev_alloc(&A->carry_row, tiles));
+    SMVP_CUDA(dev_alloc(&A->head_val, tiles));
     SMVP_CUDA(dev_alloc(&A->carry_val, tiles));
     SMVP_LAUNCH(merge_plan_kernel, (unsigned)ceil_div64(tiles + 1, 256), 256, 0, s, A->row_ptr, A->rows, A->nnz, tile_items,
                 (int32_t)tiles, A->tile_row);
@@ -542,12 +586,13 @@ static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
     X(5, 2, 12, 1, 16)      \
     X(6, 2, 10, 1, 14)
 
-template <int WARPS, int IPT, int STAGES, int MINB>
-static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, cudaStream_t s)
+template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT>
+static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, const YFan *fanp, cudaStream_t s)
 {
     using Shape = MergeShape<32, IPT, STAGES>;
     constexpr int SMEM = WARPS * Shape::SMEM_BYTES;
-    auto kern = csr_merge_warp_kernel<WARPS, IPT, STAGES, MINB>;
+    auto kern = csr_merge_warp_kernel<WARPS, IPT, STAGES, MINB, FANOUT>;
+    const YFan fan = fanp ? *fanp : YFan();
     static thread_local int configured_dev = -1;
     static thread_local int resident = 1;
     int dev = 0;
@@ -567,9 +612,9 @@ static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, cuda
     if (grid > 0)
     {
         SMVP_LAUNCH(kern, (unsigned)grid, WARPS * 32, SMEM, s, A->row_ptr, A->col_ind, A->val, d_x, d_y, A->tile_row, A->rows,
-                    A->nnz, A->merge_tiles, A->carry_row, A->carry_val);
-        SMVP_LAUNCH(merge_fixup_kernel, (unsigned)ceil_div64(A->merge_tiles, 256), 256, 0, s, A->carry_row, A->carry_val,
-                    A->merge_tiles, A->rows, d_y);
+                    A->nnz, A->merge_tiles, A->head_val, A->carry_val, fan);
+        SMVP_LAUNCH(merge_fixup_kernel<FANOUT>, (unsigned)ceil_div64(A->merge_tiles, 256), 256, 0, s, (const int32_t *)A->tile_row,
+                    (const double *)A->head_val, (const double *)A->carry_val, A->merge_tiles, d_y, fan);
     }
     return SMVP_OK;
 }
@@ -588,15 +633,16 @@ static int wmerge_tile_items(int cfg)
     }
 }
 
-static int csr_mult_merge(smvp_csr *A, const double *d_x, double *d_y, cudaStream_t s)
+static int csr_mult_merge(smvp_csr *A, const double *d_x, double *d_y, const YFan *fan, cudaStream_t s)
 {
     const int cfg = pick_merge_cfg(A);
     SMVP_TRY(merge_plan(A, cfg, s));
     switch (cfg)
     {
-#define X(id, wp, i, st, mb) \
-    case id:                 \
-        return launch_wmerge<wp, i, st, mb>(A, d_x, d_y, s);
+#define X(id, wp, i, st, mb)                                                           \
+    case id:                                                                           \
+        return fan ? launch_wmerge<wp, i, st, mb, true>(A, d_x, d_y, fan, s)           \
+                   : launch_wmerge<wp, i, st, mb, false>(A, d_x, d_y, nullptr, s);
         SMVP_WMERGE_CFGS(X)
 #undef X
     default:
@@ -620,21 +666,41 @@ int csr_resolve_variant(const smvp_csr *A, int variant)
 
 using namespace smvp;
 
-extern "C" int smvp_csr_mult_device(smvp_csr *A, const double *d_x, double *d_y, int variant, void *stream)
+static int csr_mult_any(smvp_csr *A, const double *d_x, double *d_y, const YFan *fan, int variant, void *stream)
 {
-    if (!A || (A->cols > 0 && !d_x) || (A->rows > 0 && !d_y))
-        return SMVP_E_ARG;
     if (variant != SMVP_CSR_AUTO && variant != SMVP_CSR_VECTOR && variant != SMVP_CSR_MERGE)
         return SMVP_E_ARG;
     if (A->rows == 0)
         return SMVP_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const int v = csr_resolve_variant(A, variant);
-    int rc = (v == SMVP_CSR_VECTOR) ? csr_mult_vector(A, d_x, d_y, s) : csr_mult_merge(A, d_x, d_y, s);
+    int rc = (v == SMVP_CSR_VECTOR) ? csr_mult_vector(A, d_x, d_y, fan, s) : csr_mult_merge(A, d_x, d_y, fan, s);
     if (rc != SMVP_OK)
         return rc;
     SMVP_CUDA(cudaGetLastError());
     return SMVP_OK;
+}
+
+extern "C" int smvp_csr_mult_device(smvp_csr *A, const double *d_x, double *d_y, int variant, void *stream)
+{
+    if (!A || (A->cols > 0 && !d_x) || (A->rows > 0 && !d_y))
+        return SMVP_E_ARG;
+    return csr_mult_any(A, d_x, d_y, nullptr, variant, stream);
+}
+
+extern "C" int smvp_csr_mult_device_fanout(smvp_csr *A, const double *d_x, double *const *d_y_list, int n_out, int variant,
+                                           void *stream)
+{
+    if (!A || (A->cols > 0 && !d_x) || !d_y_list || n_out < 1 || n_out > SMVP_MAX_FANOUT)
+        return SMVP_E_ARG;
+    YFan fan;
+    fan.n = n_out;
+    for (int k = 0; k < SMVP_MAX_FANOUT; k++)
+        fan.p[k] = k < n_out ? d_y_list[k] : nullptr;
+    for (int k = 0; k < n_out; k++)
+        if (A->rows > 0 && !fan.p[k])
+            return SMVP_E_ARG;
+    return csr_mult_any(A, d_x, fan.p[0], &fan, variant, stream);
 }
 
 extern "C" int smvp_csr_mult(smvp_csr *A, const double *x_host, double *y_host, int iters, double *ms_each, int variant)

@@ -3,8 +3,18 @@
 The reference is single-process and single-threaded; the path shards naturally with
 exactly one exchange step per format:
 
-  CSR   contiguous ROW blocks balanced by nnz; x replicated; each rank multiplies its rows; the y
-        blocks are all-gathered (NCCL allgatherv over NVLink) so every rank ends with the full y.
+  CSR   contiguous ROW blocks balanced by nnz; x replicated; each rank multiplies its rows; every rank
+        must end with the full y.  Two exchanges:
+          "multicast"  fused: y lives in symmetric memory with an NVSwitch multicast mapping and the
+                       multiply kernels store their rows straight to the multicast address, so the
+                       switch replicates each 8-byte result into every peer's y while the SpMV is still
+                       streaming; a device-side barrier closes the step.  No separate collective.
+          "p2p"        fused, unicast: same, but the kernels store each row into every rank's y through the
+                       peer mappings of the symmetric-memory buffer (fan-out of N stores per row).
+                       Measured on B200 (tools/probe_symm.py): coalesced peer stores run at ~700 GB/s,
+                       multicast stores at ~340 GB/s per sender, so p2p wins for N = 2 and multicast
+                       (egress 1/N of the data instead of (N-1)/N) from N = 4 on.
+          "nccl"       baseline: the y blocks are all-gathered by NCCL after the multiply.
   TJDS  contiguous COLUMN blocks balanced by nnz; each rank builds a local TJDS over its columns and
         needs only its slice of x; partial y vectors are combined by NCCL reduce-scatter (sum, fp64).
 
@@ -134,7 +144,7 @@ def _measured_traffic(kernel_key):
 class RowBlockCsr:
     """y = A x with A in CSR, rows cut into nnz-balanced blocks over `world` ranks."""
 
-    def __init__(self, eng, source, rank, world, variant=0, exchange="nccl"):
+    def __init__(self, eng, source, rank, world, variant=0, exchange="nccl", release_source=False):
         import torch
 
         self.eng, self.rank, self.world, self.variant, self.exchange = eng, rank, world, variant, exchange
@@ -146,21 +156,48 @@ class RowBlockCsr:
         self.A = eng.CsrMatrix.build_device(r, c, v, self.r1 - self.r0, self.N, r.n)
         for a in (r, c, v):
             a.free()
-        if hasattr(source, "release") and world == 1:
+        if hasattr(source, "release") and release_source:
             source.release()
         self.global_nnz = source.nnz
         self.global_bytes_per_mult = 12 * source.nnz + 4 * (self.M + 1) + 8 * self.N + 8 * self.M
         self.local_bytes_per_mult = self.A.bytes_per_mult
-        self.y_full = torch.zeros(self.M, dtype=torch.float64, device="cuda")
+        self.symm = None
+        self.y_fan = None
+        if world > 1 and exchange in ("multicast", "p2p"):
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+
+            self.y_full = symm_mem.empty(self.M, dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
+            self.y_full.zero_()
+            self.symm = symm_mem.rendezvous(self.y_full, dist.group.WORLD.group_name)
+            self.y_write = None
+            if exchange == "multicast":
+                if not self.symm.multicast_ptr:
+                    raise RuntimeError("this system exposes no NVSwitch multicast mapping; use exchange='p2p' or 'nccl'")
+                # write-only view of y: one store here lands in every rank's y_full
+                self.y_write = int(self.symm.multicast_ptr) + 8 * self.r0
+            else:
+                if world > 8:
+                    raise RuntimeError("p2p fan-out supports at most 8 ranks")
+                # my block of y inside every rank's buffer, my own first
+                ptrs = [int(p) for p in self.symm.buffer_ptrs]
+                order = [rank] + [k for k in range(world) if k != rank]
+                self.y_fan = [ptrs[k] + 8 * self.r0 for k in order]
+        else:
+            self.y_full = torch.zeros(self.M, dtype=torch.float64, device="cuda")
+            self.y_write = None
         self.y_local = self.y_full[self.r0:self.r1]
         self.local_rows_out = self.r1 - self.r0
         resolved = self.A.auto_variant if variant == eng.CSR_AUTO else variant
         self.variant_name = {eng.CSR_VECTOR: "vector", eng.CSR_MERGE: "merge"}[resolved]
         self.kernel_name = {"vector": "csr_vector_kernel", "merge": "csr_merge_warp_kernel"}[self.variant_name]
-        self.partition_desc = ("row blocks balanced by nnz, %d ranks; x replicated; y %s" %
-                               (world, "all-gathered over NCCL" if (world > 1 and exchange == "nccl") else "kept local"))
+        how = {"nccl": "all-gathered over NCCL", "multicast": "stored by the SpMV kernel to the NVSwitch multicast "
+               "address of y (fused, no collective) + device barrier",
+               "p2p": "stored by the SpMV kernel into every rank's y through NVLink peer mappings (fused, no collective) "
+               "+ device barrier", "none": "kept local"}[exchange if world > 1 else "none"]
+        self.partition_desc = "row blocks balanced by nnz, %d ranks; x replicated; y %s" % (world, how)
         self.e2e_api = ("smvp_csr_mult(A, x_host, y_host, iters=1) [C ABI, pinned host buffers]" if world == 1 else
-                        "H2D x -> smvp_csr_mult_device -> NCCL allgather -> D2H y block")
+                        "H2D x -> smvp_csr_mult_device -> %s -> D2H y block" % how)
         self.x = None
         self._source_desc = source.desc
 
@@ -168,13 +205,18 @@ class RowBlockCsr:
         self.x = x
 
     def multiply(self, stream=None):
-        self.A.mult_device(self.x, self.y_local, self.variant, stream)
+        if self.y_fan is not None:
+            self.A.mult_device_fanout(self.x, self.y_fan, self.variant, stream)
+        else:
+            self.A.mult_device(self.x, self.y_write if self.y_write is not None else self.y_local, self.variant, stream)
 
     def exchange_y(self, stream=None):
         if self.world > 1 and self.exchange == "nccl":
             import torch.distributed as dist
 
             allgather_v(dist, self.y_full, self.bounds, self.rank)
+        elif self.symm is not None:
+            self.symm.barrier(channel=0)  # every rank's stores have landed everywhere
 
     def step(self, stream=None):
         self.multiply(stream)
@@ -206,7 +248,7 @@ class RowBlockCsr:
 class ColBlockTjds:
     """y = A x with A in TJDS, columns cut into nnz-balanced blocks over `world` ranks; partial y reduce-scattered."""
 
-    def __init__(self, eng, source, rank, world, variant=0, exchange="nccl"):
+    def __init__(self, eng, source, rank, world, variant=0, exchange="nccl", release_source=False):
         import torch
 
         self.eng, self.rank, self.world, self.variant, self.exchange = eng, rank, world, variant, exchange
@@ -218,7 +260,7 @@ class ColBlockTjds:
         self.T = eng.TjdsMatrix.build_device(r, c, v, self.M, self.c1 - self.c0, r.n)
         for a in (r, c, v):
             a.free()
-        if hasattr(source, "release") and world == 1:
+        if hasattr(source, "release") and release_source:
             source.release()
         self.global_nnz = source.nnz
         # ndiag of the whole matrix is the max over ranks of the local ndiag

@@ -72,6 +72,7 @@ SIGNATURES = {
     "smvp_csr_build_device": (_int, [_vp, _vp, _vp, _i32, _i32, _i64, _pp]),
     "smvp_tjds_build_device": (_int, [_vp, _vp, _vp, _i32, _i32, _i64, _pp]),
     "smvp_csr_mult_device": (_int, [_vp, _vp, _vp, _int, _vp]),
+    "smvp_csr_mult_device_fanout": (_int, [_vp, _vp, _vp, _int, _int, _vp]),
     "smvp_tjds_set_x_device": (_int, [_vp, _vp, _vp]),
     "smvp_tjds_mult_device": (_int, [_vp, _vp, _int, _i32, _vp]),
     "smvp_csr_info": (_int, [_vp, ctypes.POINTER(_CsrInfo)]),
@@ -234,6 +235,12 @@ class CsrMatrix:
 
     def mult_device(self, d_x, d_y, variant=CSR_AUTO, stream=None):
         _check(lib().smvp_csr_mult_device(self._h, _ptr(d_x), _ptr(d_y), variant, _stream(stream)), "smvp_csr_mult_device")
+
+    def mult_device_fanout(self, d_x, y_ptrs, variant=CSR_AUTO, stream=None):
+        """y = A x stored into every destination of y_ptrs (device addresses, possibly peer-mapped)."""
+        arr = (ctypes.c_void_p * len(y_ptrs))(*[int(p) for p in y_ptrs])
+        _check(lib().smvp_csr_mult_device_fanout(self._h, _ptr(d_x), arr, len(y_ptrs), variant, _stream(stream)),
+               "smvp_csr_mult_device_fanout")
 
     def export(self):
         row_ptr = np.zeros(self.rows + 1, np.int32)

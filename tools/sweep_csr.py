@@ -53,7 +53,7 @@ def main():
         src = sdist.StencilSource(eng, args.grid, args.grid, args.grid)
     else:
         src = sdist.RmatSource(eng, args.scale, args.edge_factor << args.scale)
-    op = sdist.RowBlockCsr(eng, src, 0, 1, eng.CSR_VECTOR, exchange="none")
+    op = sdist.RowBlockCsr(eng, src, 0, 1, eng.CSR_VECTOR, exchange="none", release_source=True)
     N = src.cols
     x = torch.empty(N, dtype=torch.float64, device="cuda")
     eng.synth_vector(x, N, 999)
