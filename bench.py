@@ -44,8 +44,9 @@ def parse_args():
     p.add_argument("--edge-factor", type=int, default=16)
     p.add_argument("--format", default="csr", choices=["csr", "tjds"])
     p.add_argument("--variant", default="auto", choices=["auto", "vector", "merge", "atomic", "deterministic"])
-    p.add_argument("--exchange", default="auto", choices=["auto", "multicast", "p2p", "nccl", "none"],
+    p.add_argument("--exchange", default="auto", choices=["auto", "copy", "multicast", "p2p", "nccl", "none"],
                    help="N>1: collective after the multiply (allgather of y for CSR, reduce-scatter for TJDS)")
+    p.add_argument("--sub-blocks", type=int, default=4, help="exchange=copy: sub-blocks per rank")
     p.add_argument("--cpu-grid", type=int, default=100, help="grid edge of the bounded CPU sample (stencil27)")
     p.add_argument("--cpu-scale", type=int, default=20, help="scale of the bounded CPU sample (rmat)")
     p.add_argument("--cpu-iters", type=int, default=10)
@@ -270,14 +271,15 @@ def run_ours(args):
         gen = sdist.RmatSource(eng, args.scale, args.edge_factor << args.scale)
     exch = "none" if world == 1 else args.exchange
     if args.format == "csr":
-        # "auto": the fused paths first (measured on B200, profiles/: in-kernel multicast stores beat in-kernel
-        # unicast fan-out, both beat SpMV followed by an NCCL allgather), NCCL as the fallback of last resort
-        candidates = ["multicast", "p2p", "nccl"] if exch == "auto" else [exch]
+        # "auto", in the order measured on B200 (profiles/r01_multigpu.md): copy engines pushing finished
+        # sub-blocks over NVLink while the next sub-block multiplies; in-kernel stores to the NVSwitch multicast
+        # address; in-kernel unicast fan-out; SpMV followed by an NCCL allgather as the fallback of last resort
+        candidates = ["copy", "multicast", "p2p", "nccl"] if exch == "auto" else [exch]
         op, err = None, None
         for cand in candidates:
             try:
                 op = sdist.RowBlockCsr(eng, gen, rank, world, variant_map.get(args.variant, eng.CSR_AUTO), exchange=cand,
-                                       release_source=(cand == candidates[-1]))
+                                       release_source=(cand == candidates[-1]), sub_blocks=args.sub_blocks)
             except Exception as e:  # noqa: BLE001  (e.g. no NVSwitch multicast on this box)
                 op, err = None, e
             if world > 1:
@@ -293,7 +295,7 @@ def run_ours(args):
             raise err if err is not None else RuntimeError("no exchange could be set up on every rank")
     else:
         op = sdist.ColBlockTjds(eng, gen, rank, world, tj_map.get(args.variant, eng.TJDS_ATOMIC),
-                                exchange="nccl" if exch in ("multicast", "p2p", "nccl") else "none", release_source=True)
+                                exchange="nccl" if exch in ("copy", "multicast", "p2p", "nccl") else "none", release_source=True)
     torch.cuda.synchronize()
     build_s = time.time() - t_build0
     nnz_total = op.global_nnz

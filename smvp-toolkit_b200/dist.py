@@ -14,6 +14,14 @@ exactly one exchange step per format:
                        Measured on B200 (tools/probe_symm.py): coalesced peer stores run at ~700 GB/s,
                        multicast stores at ~340 GB/s per sender, so p2p wins for N = 2 and multicast
                        (egress 1/N of the data instead of (N-1)/N) from N = 4 on.
+          "copy"       pipelined: the rank's row block is cut into sub-blocks (nnz-balanced); while the SpMV
+                       of sub-block k+1 streams the matrix on the SMs, the copy engines push the finished
+                       rows of sub-block k into every peer's y over NVLink (cudaMemcpyAsync to the peer
+                       mappings, no SM involved).  The exchange then costs one sub-block's copy instead
+                       of the whole allgather.  At N = 8 the allgather itself is NVLink-ingress bound
+                       (each GPU must receive 7/8 of y: 352 MB = 0.55 ms measured), so large aligned
+                       transfers matter more than fusing: in-kernel 8-byte stores reach only a third of
+                       that rate.
           "nccl"       baseline: the y blocks are all-gathered by NCCL after the multiply.
   TJDS  contiguous COLUMN blocks balanced by nnz; each rank builds a local TJDS over its columns and
         needs only its slice of x; partial y vectors are combined by NCCL reduce-scatter (sum, fp64).
@@ -55,7 +63,43 @@ def bounds_from_counts(counts, parts):
 def allgather_v(dist, y_full, bounds, rank):
     """All-gather of uneven contiguous blocks of y_full (block g = y_full[bounds[g]:bounds[g+1]]), in place."""
     views = [y_full[bounds[g]:bounds[g + 1]] for g in range(len(bounds) - 1)]
-    dist.all_gather(views, views[rank])
+    if dist.get_backend() == "nccl":
+        dist.all_gather(views, views[rank])
+    else:  # gloo (CPU tests): one broadcast per block
+        for g, v in enumerate(views):
+            if v.numel() > 0:
+                dist.broadcast(v, src=g)
+
+
+def reduce_scatter_sum(dist, y_owned, y_partial, rank):
+    """y_owned = block `rank` of sum over ranks of y_partial (len(y_partial) == world * len(y_owned))."""
+    if dist.get_backend() == "nccl":
+        dist.reduce_scatter_tensor(y_owned, y_partial, op=dist.ReduceOp.SUM)
+    else:  # gloo has no reduce-scatter: all-reduce, keep my block
+        dist.all_reduce(y_partial, op=dist.ReduceOp.SUM)
+        n = y_owned.numel()
+        y_owned.copy_(y_partial[rank * n:(rank + 1) * n])
+
+
+def row_block_spmv(dist, local_mult, bounds, rank, x, y_full):
+    """The row-partitioned product, backend-agnostic: y_full[block] = local_mult(x) on every rank, then the
+    blocks are all-gathered.  local_mult maps the replicated x to this rank's rows of y."""
+    y_full[bounds[rank]:bounds[rank + 1]] = local_mult(x)
+    allgather_v(dist, y_full, bounds, rank)
+    return y_full
+
+
+def col_block_spmv(dist, local_mult, bounds, rank, world, x, rows):
+    """The column-partitioned product, backend-agnostic: partial = local_mult(x[my columns]) has `rows`
+    entries on every rank; the partials are summed and scattered (rank g owns rows [g*p, (g+1)*p))."""
+    import torch
+
+    per = -(-rows // world)
+    partial = torch.zeros(per * world, dtype=torch.float64, device=x.device)
+    partial[:rows] = local_mult(x[bounds[rank]:bounds[rank + 1]])
+    owned = torch.zeros(per, dtype=torch.float64, device=x.device)
+    reduce_scatter_sum(dist, owned, partial, rank)
+    return owned
 
 
 # ------------------------------------------------------------------------------------ matrix sources
@@ -144,26 +188,41 @@ def _measured_traffic(kernel_key):
 class RowBlockCsr:
     """y = A x with A in CSR, rows cut into nnz-balanced blocks over `world` ranks."""
 
-    def __init__(self, eng, source, rank, world, variant=0, exchange="nccl", release_source=False):
+    def __init__(self, eng, source, rank, world, variant=0, exchange="nccl", release_source=False, sub_blocks=4):
         import torch
 
         self.eng, self.rank, self.world, self.variant, self.exchange = eng, rank, world, variant, exchange
         self.M, self.N = source.rows, source.cols
         self.bounds = balanced_bounds(source.row_prefix, self.M, world)
         self.r0, self.r1 = self.bounds[rank], self.bounds[rank + 1]
-        r, c, v = source.row_block(self.r0, self.r1)
-        self.local_nnz = r.n
-        self.A = eng.CsrMatrix.build_device(r, c, v, self.r1 - self.r0, self.N, r.n)
-        for a in (r, c, v):
-            a.free()
+        # sub-blocks (only the "copy" exchange uses more than one)
+        nsub = sub_blocks if (world > 1 and exchange == "copy") else 1
+        base = source.row_prefix(self.r0)
+        if nsub > 1:
+            rel = balanced_bounds(lambda k: source.row_prefix(self.r0 + k) - base, self.r1 - self.r0, nsub)
+            self.sub_bounds = [self.r0 + b for b in rel]
+        else:
+            self.sub_bounds = [self.r0, self.r1]
+        self.subs = []
+        self.local_nnz = 0
+        for g in range(len(self.sub_bounds) - 1):
+            a0, a1 = self.sub_bounds[g], self.sub_bounds[g + 1]
+            r, c, v = source.row_block(a0, a1)
+            self.local_nnz += r.n
+            self.subs.append(eng.CsrMatrix.build_device(r, c, v, a1 - a0, self.N, r.n))
+            for a in (r, c, v):
+                a.free()
+        self.A = self.subs[0]
         if hasattr(source, "release") and release_source:
             source.release()
         self.global_nnz = source.nnz
         self.global_bytes_per_mult = 12 * source.nnz + 4 * (self.M + 1) + 8 * self.N + 8 * self.M
-        self.local_bytes_per_mult = self.A.bytes_per_mult
+        self.local_bytes_per_mult = (12 * self.local_nnz + 4 * (self.r1 - self.r0 + 1) + 8 * self.N +
+                                     8 * (self.r1 - self.r0))
         self.symm = None
         self.y_fan = None
-        if world > 1 and exchange in ("multicast", "p2p"):
+        self.peer_views, self.copy_stream, self.sub_events = None, None, None
+        if world > 1 and exchange in ("multicast", "p2p", "copy"):
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm_mem
 
@@ -176,6 +235,12 @@ class RowBlockCsr:
                     raise RuntimeError("this system exposes no NVSwitch multicast mapping; use exchange='p2p' or 'nccl'")
                 # write-only view of y: one store here lands in every rank's y_full
                 self.y_write = int(self.symm.multicast_ptr) + 8 * self.r0
+            elif exchange == "copy":
+                self.peer_views = [self.symm.get_buffer(k, (self.M,), torch.float64) for k in range(world) if k != rank]
+                # one copy stream per peer: the copy engines work on all peers at once
+                self.copy_streams = [torch.cuda.Stream() for _ in self.peer_views]
+                self.copy_stream = self.copy_streams[0]
+                self.sub_events = [torch.cuda.Event() for _ in self.subs]
             else:
                 if world > 8:
                     raise RuntimeError("p2p fan-out supports at most 8 ranks")
@@ -194,7 +259,10 @@ class RowBlockCsr:
         how = {"nccl": "all-gathered over NCCL", "multicast": "stored by the SpMV kernel to the NVSwitch multicast "
                "address of y (fused, no collective) + device barrier",
                "p2p": "stored by the SpMV kernel into every rank's y through NVLink peer mappings (fused, no collective) "
-               "+ device barrier", "none": "kept local"}[exchange if world > 1 else "none"]
+               "+ device barrier",
+               "copy": "pushed to every rank by the copy engines over NVLink, sub-block by sub-block, while the next "
+               "sub-block's SpMV runs (%d sub-blocks) + device barrier" % len(self.subs),
+               "none": "kept local"}[exchange if world > 1 else "none"]
         self.partition_desc = "row blocks balanced by nnz, %d ranks; x replicated; y %s" % (world, how)
         self.e2e_api = ("smvp_csr_mult(A, x_host, y_host, iters=1) [C ABI, pinned host buffers]" if world == 1 else
                         "H2D x -> smvp_csr_mult_device -> %s -> D2H y block" % how)
@@ -205,8 +273,20 @@ class RowBlockCsr:
         self.x = x
 
     def multiply(self, stream=None):
+        import torch
+
         if self.y_fan is not None:
             self.A.mult_device_fanout(self.x, self.y_fan, self.variant, stream)
+        elif self.peer_views is not None:
+            main = stream if stream is not None else torch.cuda.current_stream()
+            for g, A in enumerate(self.subs):
+                a0, a1 = self.sub_bounds[g], self.sub_bounds[g + 1]
+                A.mult_device(self.x, self.y_full[a0:a1], self.variant, main)
+                self.sub_events[g].record(main)
+                for pv, cs in zip(self.peer_views, self.copy_streams):
+                    with torch.cuda.stream(cs):
+                        cs.wait_event(self.sub_events[g])
+                        pv[a0:a1].copy_(self.y_full[a0:a1], non_blocking=True)
         else:
             self.A.mult_device(self.x, self.y_write if self.y_write is not None else self.y_local, self.variant, stream)
 
@@ -216,6 +296,12 @@ class RowBlockCsr:
 
             allgather_v(dist, self.y_full, self.bounds, self.rank)
         elif self.symm is not None:
+            if self.copy_stream is not None:
+                import torch
+
+                main = stream if stream is not None else torch.cuda.current_stream()
+                for cs in self.copy_streams:
+                    main.wait_stream(cs)
             self.symm.barrier(channel=0)  # every rank's stores have landed everywhere
 
     def step(self, stream=None):
@@ -241,8 +327,9 @@ class RowBlockCsr:
         return _measured_traffic(self.kernel_name)
 
     def free(self):
-        self.A.free()
-        self.y_full = self.y_local = None
+        for A in self.subs:
+            A.free()
+        self.y_full = self.y_local = self.peer_views = None
 
 
 class ColBlockTjds:
@@ -297,7 +384,7 @@ class ColBlockTjds:
         if self.world > 1 and self.exchange == "nccl":
             import torch.distributed as dist
 
-            dist.reduce_scatter_tensor(self.y_owned, self.y_partial, op=dist.ReduceOp.SUM)
+            reduce_scatter_sum(dist, self.y_owned, self.y_partial, self.rank)
 
     def step(self, stream=None):
         self.multiply(stream)

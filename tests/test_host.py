@@ -1,0 +1,140 @@
+"""CPU tests of the C host side (smvp-toolkit_b200/host): Matrix Market loader and report writer, through
+libsmvp_host.so, against the reference's fixtures."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+from oracle import oracle
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(REPO, "smvp-toolkit_b200", "lib")
+
+
+class TimeStats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in ("time_total", "time_avg", "time_stdev", "time_min", "time_max")]
+
+
+@pytest.fixture(scope="module")
+def host():
+    so = os.path.join(LIB, "libsmvp_host.so")
+    if not os.path.exists(so):
+        import __graft_entry__
+
+        __graft_entry__.build()
+    L = ctypes.CDLL(so)
+    L.smvp_load_mtx.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_void_p)]
+    L.smvp_load_mtx.restype = ctypes.c_int
+    L.smvp_mmio_error_text.argtypes = [ctypes.c_int]
+    L.smvp_mmio_error_text.restype = ctypes.c_char_p
+    L.smvp_write_report.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_void_p, ctypes.POINTER(TimeStats), ctypes.c_ulong, ctypes.c_char_p, ctypes.c_size_t]
+    L.smvp_write_report.restype = ctypes.c_int
+    return L
+
+
+def load(host, path):
+    code = ctypes.create_string_buffer(4)
+    m, n, nnz, p = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64(), ctypes.c_void_p()
+    rc = host.smvp_load_mtx(path.encode(), code, ctypes.byref(m), ctypes.byref(n), ctypes.byref(nnz), ctypes.byref(p))
+    if rc != 0:
+        return rc, None
+    buf = (ctypes.c_char * (16 * nnz.value)).from_address(p.value)
+    coo = np.frombuffer(buf, dtype=oracle.COO_DT, count=nnz.value).copy()
+    ctypes.CDLL(None).free(p)
+    return 0, (m.value, n.value, coo, code.raw.decode())
+
+
+@pytest.mark.parametrize("name", util.SAMPLES)
+def test_loader_matches_reference_semantics(host, name):
+    """1-based -> 0-based, pattern => 1.0, symmetric NOT expanded (main-cli.c:1427-1441)."""
+    rc, got = load(host, util.sample_path(name))
+    assert rc == 0
+    m, n, coo, code = got
+    em, en, ecoo = util.load_sample(name)
+    assert (m, n) == (em, en)
+    assert np.array_equal(coo["row"], ecoo["row"]) and np.array_equal(coo["col"], ecoo["col"])
+    assert np.array_equal(coo["val"], ecoo["val"])
+    assert code[0] == "M" and code[1] == "C"
+    if name == "pwt":
+        assert code == "MCPS" and len(coo) == 181313  # stored triangle only
+
+
+def test_loader_error_paths(host, tmp_path):
+    rc, _ = load(host, util.sample_path("badfile"))  # 0-byte fixture of the reference
+    assert rc == 12  # MM_PREMATURE_EOF
+    assert b"Required parameters not present on first line" in host.smvp_mmio_error_text(rc)
+    rc, _ = load(host, str(tmp_path / "missing.mtx"))
+    assert rc == 101
+    cases = {
+        "nohdr.mtx": ("hello matrix coordinate real general\n1 1 1\n1 1 2.0\n", 14),
+        "badtype.mtx": ("%%MatrixMarket matrix coordinate quaternion general\n1 1 1\n1 1 2.0\n", 15),
+        "dense.mtx": ("%%MatrixMarket matrix array real general\n1 1\n2.0\n", 102),
+        "complex.mtx": ("%%MatrixMarket matrix coordinate complex general\n1 1 1\n1 1 2.0 0.0\n", 103),
+        "short.mtx": ("%%MatrixMarket matrix coordinate real general\n2 2 3\n1 1 2.0\n2 2 1.0\n", 104),
+    }
+    for fn, (text, want) in cases.items():
+        p = tmp_path / fn
+        p.write_text(text)
+        rc, _ = load(host, str(p))
+        assert rc == want, fn
+
+
+def test_loader_comments_integer_and_blank_lines(host, tmp_path):
+    p = tmp_path / "c.mtx"
+    p.write_text("%%MatrixMarket MATRIX Coordinate Integer General\n% a comment\n%another\n\n3 4 2\n1 4 7\n\n3 1 -2\n")
+    rc, got = load(host, str(p))
+    assert rc == 0
+    m, n, coo, code = got
+    assert (m, n) == (3, 4) and code == "MCIG"
+    assert coo["row"].tolist() == [0, 2] and coo["col"].tolist() == [3, 0] and coo["val"].tolist() == [7.0, -2.0]
+
+
+@pytest.mark.parametrize("name,alg", sorted(util.GOLDEN_REPORTS))
+def test_report_writer_reproduces_golden_files(host, tmp_path, name, alg):
+    """Same header, same layout, same %g formatting as generateReportText (main-cli.c:294-316): with the golden
+    file's own numbers the writer must reproduce it byte for byte."""
+    gpath = os.path.join(util.GOLDEN, "reports", util.GOLDEN_REPORTS[(name, alg)])
+    rep = util.parse_report(gpath)
+    golden = open(gpath).read()
+    lines = golden.split("\n")
+    unix_time = int(lines[1].split()[2])
+    in_name = lines[4]
+    st = TimeStats(rep["total"], rep["avg"], rep["stdev"], rep["min"], rep["max"])
+    m, n, coo = util.load_sample(name)
+    y = oracle.csr_mult(*oracle.csr_build(coo, m, n), np.ones(n)) if alg == "CSR" else oracle.tjds_mult_ref_compat(
+        oracle.tjds_build(coo, m, n))
+    y = np.ascontiguousarray(y)
+    out = ctypes.create_string_buffer(4096)
+    rc = host.smvp_write_report(in_name.encode(), str(tmp_path).encode(), alg.encode(), rep["nnz"], m, rep["iters"],
+                                y.ctypes.data_as(ctypes.c_void_p), ctypes.byref(st), unix_time, out, 4096)
+    assert rc == 0
+    path = out.value.decode()
+    assert os.path.basename(path) == os.path.basename(gpath)
+    assert open(path).read() == golden
+
+
+def test_cli_usage_and_option_errors():
+    cli = os.path.join(LIB, "smvp-toolkit-cli")
+    if not os.path.exists(cli):
+        pytest.skip("CLI not built")
+    r = subprocess.run([cli], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage:" in r.stderr
+    r = subprocess.run([cli, "-a", "-c", "x.mtx"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Combining [-a|--all] with other algorithm flags is not supported." in r.stdout
+    r = subprocess.run([cli, "-c", "-n", "0", "x.mtx"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Invalid number of algorithm iterations specified." in r.stdout
+    r = subprocess.run([cli, "-c", "-n", "12x", "x.mtx"], capture_output=True, text=True)
+    assert r.returncode == 1 and "non-number characters" in r.stdout
+    r = subprocess.run([cli, "-c", "-d", "/nonexistent-dir", "x.mtx"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Report output folder not found" in r.stdout
+    r = subprocess.run([cli, "-c", "/nonexistent.mtx"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Specified input file not found." in r.stdout
+    r = subprocess.run([cli, "-c", util.sample_path("badfile")], capture_output=True, text=True)
+    assert r.returncode == 1 and "Required parameters not present on first line of file." in r.stdout
+    r = subprocess.run([cli, "-c", "a.mtx", "b.mtx"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Must specify a single input file" in r.stderr

@@ -32,7 +32,7 @@ def main():
         torch.cuda.synchronize()
         y_ref = whole.y_full.clone()
         nrm = float(torch.linalg.norm(y_ref))
-        for exch in ("nccl", "multicast", "p2p"):
+        for exch in ("nccl", "multicast", "p2p", "copy"):
             for variant in (eng.CSR_VECTOR, eng.CSR_MERGE):
                 try:
                     op = sdist.RowBlockCsr(eng, src, rank, world, variant, exchange=exch)
