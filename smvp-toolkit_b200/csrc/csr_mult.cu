@@ -81,6 +81,46 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                  : "memory");
 }
 
+// Tuning switches, A/B-tested on B200 (profiles/r01_logs/ab_variants.log, stencil 369^3, ms per SpMV):
+//   all off 2.995 | explicit 32-bit ld.shared 2.984 | + warp-uniform fast path for regular tiles 3.13 |
+//   + clamped (unpredicated) gathers 3.20 | + early-exit stitch scan 3.26 | all on 3.22
+// i.e. the kernel is latency- not instruction-bound: every extra vote / branch costs more than the
+// instructions it saves.  The defaults are the measured winner; the others stay for future re-tests.
+#ifndef SMVP_ASM_LDS
+#define SMVP_ASM_LDS 1
+#endif
+#ifndef SMVP_CLAMP_GATHER
+#define SMVP_CLAMP_GATHER 0
+#endif
+#ifndef SMVP_FAST_PATH
+#define SMVP_FAST_PATH 0
+#endif
+#ifndef SMVP_SCAN_EXIT
+#define SMVP_SCAN_EXIT 0
+#endif
+
+// explicit shared-window loads with 32-bit addresses (one register per view instead of a 64-bit generic pointer)
+__device__ __forceinline__ double lds_f64(uint32_t a)
+{
+#if SMVP_ASM_LDS
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+#else
+    return *reinterpret_cast<const double *>(__cvta_shared_to_generic(a));
+#endif
+}
+__device__ __forceinline__ int32_t lds_s32(uint32_t a)
+{
+#if SMVP_ASM_LDS
+    int32_t v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+#else
+    return *reinterpret_cast<const int32_t *>(__cvta_shared_to_generic(a));
+#endif
+}
+
 // ------------------------------------------------------------------ where y goes
 // Single GPU: one pointer.  Multi GPU (row blocks): every rank must end with the whole y, so
 // the multiply kernels store each finished row straight into every peer's copy of y over NVLink
@@ -233,15 +273,15 @@ struct TileView
     uint32_t vb, cb, rb;    // bytes staged of each
 };
 
-__device__ __forceinline__ TileView make_tile(const int32_t *__restrict__ tile_row, int32_t t, int32_t tile_items, int64_t total)
+// (r0, r1) = rows consumed before the tile / before the next tile (tile_row[t], tile_row[t+1])
+__device__ __forceinline__ TileView make_tile(int32_t r0, int32_t r1, int32_t t, int32_t tile_items, int64_t total)
 {
     TileView v;
     const int64_t d0 = (int64_t)t * tile_items;
     int64_t d1 = d0 + tile_items;
     if (d1 > total)
         d1 = total;
-    v.r0 = tile_row[t];
-    const int32_t r1 = tile_row[t + 1];
+    v.r0 = r0;
     v.rows_t = r1 - v.r0;
     v.n0 = d0 - v.r0;
     const int64_t n1 = d1 - r1;
@@ -267,81 +307,79 @@ template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     csr_merge_warp_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_ind, const double *__restrict__ val,
                           const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int32_t rows,
-                          int64_t nnz, int32_t num_tiles, double *__restrict__ head_val, double *__restrict__ carry_val, const __grid_constant__ YFan fan)
+                          int64_t nnz, int32_t num_tiles, double *__restrict__ head_val, double *__restrict__ carry_val,
+                          const __grid_constant__ YFan fan)
 {
-    using Shape = MergeShape<32, IPT, STAGES>;
+    static_assert(STAGES == 1, "one stage per warp: deeper rings lost to more resident warps in every sweep");
+    using Shape = MergeShape<32, IPT, 1>;
     extern __shared__ __align__(128) unsigned char stage_mem[];
-    __shared__ __align__(8) uint64_t full_bar[WARPS * STAGES];
+    __shared__ __align__(8) uint64_t full_bar[WARPS];
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t total = (int64_t)rows + nnz;
-    unsigned char *my_stages = stage_mem + (size_t)w * Shape::SMEM_BYTES;
-    uint64_t *my_bar = &full_bar[w * STAGES];
+    unsigned char *base = stage_mem + (size_t)w * Shape::SMEM_BYTES;
+    uint64_t *my_bar = &full_bar[w];
     uint64_t policy = 0;
     if (lane == 0)
     {
-#pragma unroll
-        for (int s = 0; s < STAGES; s++)
-            mbar_init(&my_bar[s], 1);
+        mbar_init(my_bar, 1);
         fence_mbar_init();
         policy = l2_evict_first_policy();
     }
     __syncwarp();
 
-    const int64_t warp_stride = (int64_t)gridDim.x * WARPS;
-    const int64_t first_tile = (int64_t)blockIdx.x * WARPS + w;
-
-    auto issue = [&](const TileView &v, int s) { // lane 0 only
-        unsigned char *base = my_stages + (size_t)s * Shape::STAGE_BYTES;
-        mbar_expect_tx(&my_bar[s], v.vb + v.cb + v.rb);
+    const int32_t warp_stride = (int32_t)gridDim.x * WARPS;
+    auto issue = [&](const TileView &v) { // lane 0 only
+        mbar_expect_tx(my_bar, v.vb + v.cb + v.rb);
         if (v.vb)
-            bulk_g2s(base, val + v.va, v.vb, &my_bar[s], policy);
+            bulk_g2s(base, val + v.va, v.vb, my_bar, policy);
         if (v.cb)
-            bulk_g2s(base + v.vb, col_ind + v.ca, v.cb, &my_bar[s], policy);
+            bulk_g2s(base + v.vb, col_ind + v.ca, v.cb, my_bar, policy);
         if (v.rb)
-            bulk_g2s(base + v.vb + v.cb, row_ptr + v.ra, v.rb, &my_bar[s], policy);
+            bulk_g2s(base + v.vb + v.cb, row_ptr + v.ra, v.rb, my_bar, policy);
     };
 
-    // prologue: fill the ring
-    TileView ring[STAGES];
-#pragma unroll
-    for (int s = 0; s < STAGES; s++)
+    int32_t t = (int32_t)blockIdx.x * WARPS + w;
+    int32_t cur_r0 = 0, cur_r1 = 0; // merge coordinates of the tile in flight: the only tile state kept across the loop
+    if (t < num_tiles)
     {
-        const int64_t t = first_tile + (int64_t)s * warp_stride;
-        if (t < num_tiles)
-        {
-            ring[s] = make_tile(tile_row, (int32_t)t, Shape::TILE, total);
-            if (lane == 0)
-                issue(ring[s], s);
-        }
+        cur_r0 = __ldg(tile_row + t);
+        cur_r1 = __ldg(tile_row + t + 1);
+        if (lane == 0)
+            issue(make_tile(cur_r0, cur_r1, t, Shape::TILE, total));
     }
+    uint32_t parity = 0;
 
-    int k = 0;
-    for (int64_t t64 = first_tile; t64 < num_tiles; t64 += warp_stride, k++)
+    while (t < num_tiles)
     {
-        const int s = k % STAGES;
-        const uint32_t parity = (uint32_t)(k / STAGES) & 1u;
-        TileView v;
-#pragma unroll
-        for (int q = 0; q < STAGES; q++) // static indexing keeps the ring in registers
-            if (q == s)
-                v = ring[q];
-        unsigned char *base = my_stages + (size_t)s * Shape::STAGE_BYTES;
-        const double *sval = reinterpret_cast<const double *>(base) - v.va;
-        const int32_t *scol = reinterpret_cast<const int32_t *>(base + v.vb) - v.ca;
-        const int32_t *srow = reinterpret_cast<const int32_t *>(base + v.vb + v.cb) - v.ra;
-        auto row_end = [&](int32_t i) -> int32_t { return srow[v.r0 + 1 + i] - (int32_t)v.n0; };
+        // per-tile scalars: only what the walk needs stays live (the rest of the TileView dies here)
+        int32_t n0, tile_r0, rows_t, nnz_t, items_t;
+        uint32_t sval, scol, srow; // shared-window byte addresses of TILE-LOCAL nonzero 0 / row 0
+        {
+            const TileView v = make_tile(cur_r0, cur_r1, t, Shape::TILE, total);
+            n0 = (int32_t)v.n0;
+            tile_r0 = v.r0;
+            rows_t = v.rows_t;
+            nnz_t = v.nnz_t;
+            items_t = v.items_t;
+            const uint32_t b = smem_u32(base);
+            sval = b + 8u * (uint32_t)(n0 - v.va);
+            scol = b + v.vb + 4u * (uint32_t)(n0 - v.ca);
+            srow = b + v.vb + v.cb + 4u * (uint32_t)(v.r0 + 1 - v.ra);
+        }
+        auto row_end = [&](int32_t i) -> int32_t { return lds_s32(srow + 4u * (uint32_t)i) - n0; };
 
-        mbar_wait(&my_bar[s], parity);
+        mbar_wait(my_bar, parity);
+        parity ^= 1u;
 
         // ---- my first merge item: interpolate, gallop, bisect (2 probes on regular matrices)
         int32_t d = lane * IPT;
-        if (d > v.items_t)
-            d = v.items_t;
-        int32_t lo = d > v.nnz_t ? d - v.nnz_t : 0, hi = d < v.rows_t ? d : v.rows_t;
+        if (d > items_t)
+            d = items_t;
+        int32_t lo = d > nnz_t ? d - nnz_t : 0, hi = d < rows_t ? d : rows_t;
         if (lo < hi)
         {
-            int32_t g = (int32_t)(((int64_t)d * v.rows_t) / v.items_t);
+            int32_t g = (int32_t)(((uint32_t)d * (uint32_t)rows_t) / (uint32_t)items_t); // < 2^20: 32-bit is exact
             g = g < lo ? lo : (g > hi - 1 ? hi - 1 : g);
             int32_t step = 1;
             if (row_end(g) <= d - g - 1)
@@ -391,94 +429,140 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         }
         const int32_t i0 = lo, j0 = d - lo;
         int32_t d_next = (lane + 1) * IPT;
-        if (d_next > v.items_t)
-            d_next = v.items_t;
+        if (d_next > items_t)
+            d_next = items_t;
         int32_t j_next = __shfl_down_sync(0xffffffffu, j0, 1);
         if (lane == 31)
-            j_next = v.nnz_t;
+            j_next = nnz_t;
         const int32_t i_next = d_next - j_next;
         const int32_t cnt = j_next - j0;
 
-        // ---- all my gathers first
+        // ---- all my gathers first: IPT independent loads in flight per lane.  Indices are clamped instead of
+        // predicated (a lane with fewer than IPT nonzeros re-reads the tile's last one and ignores the product).
         double prod[IPT];
+#if SMVP_CLAMP_GATHER
+        if (nnz_t > 0)
         {
-            const int64_t jg = v.n0 + j0;
+            const int32_t jmax = nnz_t - 1;
 #pragma unroll
             for (int q = 0; q < IPT; q++)
             {
-                prod[q] = 0.0;
-                if (q < cnt)
-                {
-                    const int32_t c = scol[jg + q];
-                    prod[q] = __dmul_rn(sval[jg + q], __ldg(x + c));
-                }
+                const uint32_t j = (uint32_t)min(j0 + q, jmax);
+                const int32_t c = lds_s32(scol + 4u * j);
+                prod[q] = __dmul_rn(lds_f64(sval + 8u * j), __ldg(x + c));
             }
         }
-
-        // ---- sequential walk of my items
-        double sum = 0.0, first_sum = 0.0;
-        bool has_first = false;
-        int32_t row = i0;
-        int32_t end = row < v.rows_t ? row_end(row) : 0x7fffffff;
+        else
+        {
+#pragma unroll
+            for (int q = 0; q < IPT; q++)
+                prod[q] = 0.0;
+        }
+#else
 #pragma unroll
         for (int q = 0; q < IPT; q++)
         {
+            prod[q] = 0.0;
             if (q < cnt)
             {
-                while (end <= j0 + q)
-                {
-                    if (!has_first)
-                    {
-                        has_first = true;
-                        first_sum = sum;
-                    }
-                    else
-                        store_y<FANOUT>(y, fan, (int64_t)v.r0 + row, sum);
-                    sum = 0.0;
-                    row++;
-                    end = row < v.rows_t ? row_end(row) : 0x7fffffff;
-                }
-                sum = __dadd_rn(sum, prod[q]);
+                const uint32_t j = (uint32_t)(j0 + q);
+                const int32_t c = lds_s32(scol + 4u * j);
+                prod[q] = __dmul_rn(lds_f64(sval + 8u * j), __ldg(x + c));
             }
         }
-        while (row < i_next)
+#endif
+
+        double sum = 0.0, first_sum = 0.0;
+        bool has_first = false;
+        const int32_t nrow = i_next - i0; // row ends among my items
+        // fast path (whole warp): every lane holds either IPT nonzeros and no row end, or IPT-1 nonzeros followed
+        // by exactly one row end -- the shape of every interior tile of a regular matrix
+#if SMVP_FAST_PATH
+        const bool simple = (nrow == 0 && cnt == IPT) || (nrow == 1 && cnt == IPT - 1 && row_end(i0) == j0 + cnt);
+        const bool all_simple = __all_sync(0xffffffffu, simple);
+#else
+        const bool all_simple = false;
+        (void)nrow;
+#endif
+        if (all_simple)
         {
-            if (!has_first)
+#pragma unroll
+            for (int q = 0; q < IPT - 1; q++)
+                sum = __dadd_rn(sum, prod[q]);
+            if (nrow == 0)
+                sum = __dadd_rn(sum, prod[IPT - 1]);
+            else
             {
                 has_first = true;
                 first_sum = sum;
+                sum = 0.0;
             }
-            else
-                store_y<FANOUT>(y, fan, (int64_t)v.r0 + row, sum);
-            sum = 0.0;
-            row++;
         }
-
-        // ---- this stage is consumed: refill it (lane 0) while the warp stitches
-        __syncwarp();
+        else
         {
-            const int64_t tn = t64 + (int64_t)STAGES * warp_stride;
-            if (tn < num_tiles)
-            {
-                const TileView nv = make_tile(tile_row, (int32_t)tn, Shape::TILE, total);
+            int32_t row = i0;
+            int32_t end = row < rows_t ? row_end(row) : 0x7fffffff;
 #pragma unroll
-                for (int q = 0; q < STAGES; q++)
-                    if (q == s)
-                        ring[q] = nv;
-                if (lane == 0)
-                    issue(nv, s);
+            for (int q = 0; q < IPT; q++)
+            {
+                if (q < cnt)
+                {
+                    while (end <= j0 + q)
+                    {
+                        if (!has_first)
+                        {
+                            has_first = true;
+                            first_sum = sum;
+                        }
+                        else
+                            store_y<FANOUT>(y, fan, (int64_t)tile_r0 + row, sum);
+                        sum = 0.0;
+                        row++;
+                        end = row < rows_t ? row_end(row) : 0x7fffffff;
+                    }
+                    sum = __dadd_rn(sum, prod[q]);
+                }
+            }
+            while (row < i_next)
+            {
+                if (!has_first)
+                {
+                    has_first = true;
+                    first_sum = sum;
+                }
+                else
+                    store_y<FANOUT>(y, fan, (int64_t)tile_r0 + row, sum);
+                sum = 0.0;
+                row++;
             }
         }
 
-        // ---- stitch rows cut by lane boundaries: segmented inclusive scan of (carry row, carry sum)
+        // ---- the stage is consumed: refill it for my next tile while the warp stitches
+        __syncwarp();
+        const int32_t tn = t + warp_stride;
+        if (tn < num_tiles && tn > t)
+        {
+            cur_r0 = __ldg(tile_row + tn);
+            cur_r1 = __ldg(tile_row + tn + 1);
+            if (lane == 0)
+                issue(make_tile(cur_r0, cur_r1, tn, Shape::TILE, total));
+        }
+
+        // ---- stitch rows cut by lane boundaries: segmented inclusive scan of (carry row, carry sum); stops as
+        // soon as no run of equal keys is longer than the distance already covered
         const int32_t key = i_next; // the row my trailing partial belongs to
         double scan = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1)
         {
-            const double pv = __shfl_up_sync(0xffffffffu, scan, o);
             const int32_t pk = __shfl_up_sync(0xffffffffu, key, o);
-            if (lane >= o && pk == key)
+            const bool take = lane >= o && pk == key;
+#if SMVP_SCAN_EXIT
+            if (!__any_sync(0xffffffffu, take))
+                break;
+#endif
+            const double pv = __shfl_up_sync(0xffffffffu, scan, o);
+            if (take)
                 scan = __dadd_rn(pv, scan);
         }
         const double prev_scan = __shfl_up_sync(0xffffffffu, scan, 1);
@@ -491,12 +575,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             // kernel, which adds the carries and writes y.  y itself is only ever WRITTEN here (never
             // read), so it may be a write-only mapping such as an NVSwitch multicast address.
             if (i0 == 0)
-                head_val[(int32_t)t64] = first_sum;
+                head_val[t] = first_sum;
             else
-                store_y<FANOUT>(y, fan, (int64_t)v.r0 + i0, first_sum);
+                store_y<FANOUT>(y, fan, (int64_t)tile_r0 + i0, first_sum);
         }
         if (lane == 31)
-            carry_val[(int32_t)t64] = scan; // partial of the row that continues into the next tile
+            carry_val[t] = scan; // partial of the row that continues into the next tile
+        if (tn <= t)
+            break; // 32-bit overflow guard
+        t = tn;
     }
 }
 
@@ -581,10 +668,10 @@ static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
     X(0, 2, 14, 1, 16)      \
     X(1, 2, 10, 1, 16)      \
     X(2, 4, 14, 1, 8)       \
-    X(3, 4, 28, 1, 5)       \
-    X(4, 2, 28, 1, 10)      \
-    X(5, 2, 12, 1, 16)      \
-    X(6, 2, 10, 1, 14)
+    X(3, 2, 12, 1, 16)      \
+    X(4, 2, 10, 1, 14)      \
+    X(5, 2, 7, 1, 16)       \
+    X(6, 2, 9, 1, 16)
 
 template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT>
 static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, const YFan *fanp, cudaStream_t s)

@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libsmvp_cuda.so")
+LIB_PATH = os.environ.get("SMVP_LIB_PATH") or os.path.join(HERE, "lib", "libsmvp_cuda.so")  # override: tuning builds only
 
 # == MMRawData (main-cli.c:42-47)
 COO_DT = np.dtype([("row", "<i4"), ("col", "<i4"), ("val", "<f8")])
