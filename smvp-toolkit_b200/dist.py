@@ -22,6 +22,11 @@ exactly one exchange step per format:
                        (each GPU must receive 7/8 of y: 352 MB = 0.55 ms measured), so large aligned
                        transfers matter more than fusing: in-kernel 8-byte stores reach only a third of
                        that rate.
+          "pipeline"   "copy" with two y buffers: the copy engines push step k's rows while step k+1 already
+                       multiplies (x is constant over the -n loop and the reference reports only the last
+                       y, main-cli.c:401, so consecutive iterations are independent).  Every step's y still
+                       reaches every rank -- one step later -- and finish() drains the pipe; the steady-state
+                       cost per step is max(SpMV, exchange) instead of their sum.
           "nccl"       baseline: the y blocks are all-gathered by NCCL after the multiply.
   TJDS  contiguous COLUMN blocks balanced by nnz; each rank builds a local TJDS over its columns and
         needs only its slice of x; partial y vectors are combined by NCCL reduce-scatter (sum, fp64).
@@ -196,6 +201,7 @@ class RowBlockCsr:
         self.bounds = balanced_bounds(source.row_prefix, self.M, world)
         self.r0, self.r1 = self.bounds[rank], self.bounds[rank + 1]
         # sub-blocks (only the "copy" exchange uses more than one)
+        # "copy" hides the exchange behind the next SUB-BLOCK; "pipeline" hides it behind the next STEP and needs none
         nsub = sub_blocks if (world > 1 and exchange == "copy") else 1
         base = source.row_prefix(self.r0)
         if nsub > 1:
@@ -222,25 +228,32 @@ class RowBlockCsr:
         self.symm = None
         self.y_fan = None
         self.peer_views, self.copy_stream, self.sub_events = None, None, None
-        if world > 1 and exchange in ("multicast", "p2p", "copy"):
+        self.nbuf, self.k = 1, 0
+        if world > 1 and exchange in ("multicast", "p2p", "copy", "pipeline"):
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm_mem
 
-            self.y_full = symm_mem.empty(self.M, dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
-            self.y_full.zero_()
-            self.symm = symm_mem.rendezvous(self.y_full, dist.group.WORLD.group_name)
+            self.nbuf = 2 if exchange == "pipeline" else 1
+            self.y_sym = symm_mem.empty(self.nbuf * self.M, dtype=torch.float64,
+                                        device=torch.device("cuda", torch.cuda.current_device()))
+            self.y_sym.zero_()
+            self.y_full = self.y_sym[:self.M]
+            self.symm = symm_mem.rendezvous(self.y_sym, dist.group.WORLD.group_name)
             self.y_write = None
             if exchange == "multicast":
                 if not self.symm.multicast_ptr:
                     raise RuntimeError("this system exposes no NVSwitch multicast mapping; use exchange='p2p' or 'nccl'")
                 # write-only view of y: one store here lands in every rank's y_full
                 self.y_write = int(self.symm.multicast_ptr) + 8 * self.r0
-            elif exchange == "copy":
-                self.peer_views = [self.symm.get_buffer(k, (self.M,), torch.float64) for k in range(world) if k != rank]
+            elif exchange in ("copy", "pipeline"):
+                self.peer_views = [self.symm.get_buffer(k, (self.nbuf * self.M,), torch.float64) for k in range(world)
+                                   if k != rank]
                 # one copy stream per peer: the copy engines work on all peers at once
                 self.copy_streams = [torch.cuda.Stream() for _ in self.peer_views]
                 self.copy_stream = self.copy_streams[0]
-                self.sub_events = [torch.cuda.Event() for _ in self.subs]
+                self.sub_events = [[torch.cuda.Event() for _ in self.subs] for _ in range(self.nbuf)]
+                self.copy_done = [[torch.cuda.Event() for _ in self.copy_streams] for _ in range(self.nbuf)]
+                self.copy_pending = [False] * self.nbuf
             else:
                 if world > 8:
                     raise RuntimeError("p2p fan-out supports at most 8 ranks")
@@ -262,6 +275,8 @@ class RowBlockCsr:
                "+ device barrier",
                "copy": "pushed to every rank by the copy engines over NVLink, sub-block by sub-block, while the next "
                "sub-block's SpMV runs (%d sub-blocks) + device barrier" % len(self.subs),
+               "pipeline": "pushed to every rank by the copy engines over NVLink (%d sub-blocks, two y buffers): step k's "
+               "exchange overlaps step k+1's SpMV, the pipe is drained inside the timed region" % len(self.subs),
                "none": "kept local"}[exchange if world > 1 else "none"]
         self.partition_desc = "row blocks balanced by nnz, %d ranks; x replicated; y %s" % (world, how)
         self.e2e_api = ("smvp_csr_mult(A, x_host, y_host, iters=1) [C ABI, pinned host buffers]" if world == 1 else
@@ -279,14 +294,21 @@ class RowBlockCsr:
             self.A.mult_device_fanout(self.x, self.y_fan, self.variant, stream)
         elif self.peer_views is not None:
             main = stream if stream is not None else torch.cuda.current_stream()
+            b = self.k % self.nbuf
+            off = b * self.M
+            if self.copy_pending[b]:  # the copies that still read this buffer (two steps ago) must be done
+                for ev in self.copy_done[b]:
+                    main.wait_event(ev)
+            self.y_full = self.y_sym[off:off + self.M]
+            self.y_local = self.y_full[self.r0:self.r1]
             for g, A in enumerate(self.subs):
-                a0, a1 = self.sub_bounds[g], self.sub_bounds[g + 1]
-                A.mult_device(self.x, self.y_full[a0:a1], self.variant, main)
-                self.sub_events[g].record(main)
+                a0, a1 = off + self.sub_bounds[g], off + self.sub_bounds[g + 1]
+                A.mult_device(self.x, self.y_sym[a0:a1], self.variant, main)
+                self.sub_events[b][g].record(main)
                 for pv, cs in zip(self.peer_views, self.copy_streams):
                     with torch.cuda.stream(cs):
-                        cs.wait_event(self.sub_events[g])
-                        pv[a0:a1].copy_(self.y_full[a0:a1], non_blocking=True)
+                        cs.wait_event(self.sub_events[b][g])
+                        pv[a0:a1].copy_(self.y_sym[a0:a1], non_blocking=True)
         else:
             self.A.mult_device(self.x, self.y_write if self.y_write is not None else self.y_local, self.variant, stream)
 
@@ -295,6 +317,12 @@ class RowBlockCsr:
             import torch.distributed as dist
 
             allgather_v(dist, self.y_full, self.bounds, self.rank)
+        elif self.exchange == "pipeline":
+            b = self.k % self.nbuf
+            for ev, cs in zip(self.copy_done[b], self.copy_streams):
+                ev.record(cs)
+            self.copy_pending[b] = True
+            self.k += 1
         elif self.symm is not None:
             if self.copy_stream is not None:
                 import torch
@@ -303,6 +331,16 @@ class RowBlockCsr:
                 for cs in self.copy_streams:
                     main.wait_stream(cs)
             self.symm.barrier(channel=0)  # every rank's stores have landed everywhere
+
+    def finish(self, stream=None):
+        """Drain whatever the exchange still has in flight (only "pipeline" defers anything)."""
+        if self.exchange == "pipeline" and self.symm is not None:
+            import torch
+
+            main = stream if stream is not None else torch.cuda.current_stream()
+            for cs in self.copy_streams:
+                main.wait_stream(cs)
+            self.symm.barrier(channel=0)
 
     def step(self, stream=None):
         self.multiply(stream)
@@ -329,7 +367,7 @@ class RowBlockCsr:
     def free(self):
         for A in self.subs:
             A.free()
-        self.y_full = self.y_local = self.peer_views = None
+        self.y_full = self.y_local = self.peer_views = self.y_sym = None
 
 
 class ColBlockTjds:
@@ -385,6 +423,9 @@ class ColBlockTjds:
             import torch.distributed as dist
 
             reduce_scatter_sum(dist, self.y_owned, self.y_partial, self.rank)
+
+    def finish(self, stream=None):
+        pass
 
     def step(self, stream=None):
         self.multiply(stream)

@@ -32,7 +32,7 @@ def main():
         torch.cuda.synchronize()
         y_ref = whole.y_full.clone()
         nrm = float(torch.linalg.norm(y_ref))
-        for exch in ("nccl", "multicast", "p2p", "copy"):
+        for exch in ("nccl", "multicast", "p2p", "copy", "pipeline"):
             for variant in (eng.CSR_VECTOR, eng.CSR_MERGE):
                 try:
                     op = sdist.RowBlockCsr(eng, src, rank, world, variant, exchange=exch)
@@ -44,6 +44,7 @@ def main():
                 for _ in range(3):
                     op.y_full.fill_(float("nan")) if exch == "nccl" else None
                     op.step(stream)
+                op.finish(stream)
                 torch.cuda.synchronize()
                 dist.barrier()
                 err = float(torch.linalg.norm(op.y_full - y_ref)) / nrm
