@@ -222,24 +222,6 @@ def workload_config(args, extra):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
-def nnz_balanced_bounds(prefix_fn, total_rows, parts):
-    """Row boundaries r_0=0 < ... < r_parts=total_rows with ~equal nnz per block."""
-    total = prefix_fn(total_rows)
-    bounds = [0]
-    for g in range(1, parts):
-        target = total * g // parts
-        lo, hi = bounds[-1], total_rows
-        while lo < hi:
-            mid = (lo + hi) // 2
-            if prefix_fn(mid) < target:
-                lo = mid + 1
-            else:
-                hi = mid
-        bounds.append(lo)
-    bounds.append(total_rows)
-    return bounds
-
-
 def run_ours(args):
     import torch
     import torch.distributed as dist

@@ -18,6 +18,8 @@
  *   --ref-compat          TJDS walks only the diagonals the SHIPPED reference loop walks (main-cli.c:865,
  *                         :1013), reproducing its golden TJDS reports; default is the full product
  *   --json                print one machine-readable line per algorithm (GB/s, GFLOP/s, variant)
+ *   --expand-symmetric    mirror the stored triangle of symmetric / skew-symmetric files (the reference multiplies
+ *                         the stored triangle only; off by default to keep report parity)
  *
  * Deliberate differences from the reference at HEAD:
  *   U1  --all-algs runs CSR and TJDS (at HEAD its mask 256 matches no algorithm bit and nothing runs);
@@ -60,7 +62,7 @@ static void usage(const char *argv0)
     fprintf(stderr,
             "Usage: %s [-acgt?] [-a|--all-algs] [-c|--csr] [-g|--cisr-gen] [-t|--tjds] [-n|--number=1000]\n"
             "        [-s|--slots=16] [-d|--dir=./] [--csr-variant=auto|vector|merge]\n"
-            "        [--tjds-variant=atomic|deterministic] [--ref-compat] [--json] [-?|--help] [--usage] [OPTIONS] <file>\n",
+            "        [--tjds-variant=atomic|deterministic] [--ref-compat] [--json] [--expand-symmetric] [-?|--help] [--usage] [OPTIONS] <file>\n",
             argv0);
 }
 
@@ -98,9 +100,10 @@ int main(int argc, char *argv[])
         {"dir", required_argument, NULL, 'd'},   {"help", no_argument, NULL, '?'},
         {"usage", no_argument, NULL, '?'},       {"csr-variant", required_argument, NULL, 1001},
         {"tjds-variant", required_argument, NULL, 1002}, {"ref-compat", no_argument, NULL, 1003},
-        {"json", no_argument, NULL, 1004},       {NULL, 0, NULL, 0}};
+        {"json", no_argument, NULL, 1004},       {"expand-symmetric", no_argument, NULL, 1005},
+        {NULL, 0, NULL, 0}};
     int alg_mode = ALG_NONE, calc_iter = 1000, cisr_slots = 16; /* defaults of main-cli.c:1258-1264 */
-    int csr_variant = SMVP_CSR_AUTO, tjds_variant = SMVP_TJDS_ATOMIC, ref_compat = 0, json = 0, all = 0;
+    int csr_variant = SMVP_CSR_AUTO, tjds_variant = SMVP_TJDS_ATOMIC, ref_compat = 0, json = 0, all = 0, expand = 0;
     const char *report_dir = "";
     const char *input;
     int c, rows = 0, cols = 0, rc, i;
@@ -173,6 +176,9 @@ int main(int argc, char *argv[])
         case 1004:
             json = 1;
             break;
+        case 1005:
+            expand = 1;
+            break;
         case ':':
             die("One or more options missing a required argument.");
             break;
@@ -198,7 +204,7 @@ int main(int argc, char *argv[])
 
     printf(ANSI_COLOR_GREEN "\n[START]\tExecuting smvp-toolbox-cli v%d.%d.%d\n" ANSI_COLOR_RESET, SMVP_MAJOR_VER, SMVP_MINOR_VER,
            SMVP_REVISION_VER);
-    rc = smvp_load_mtx(input, &matcode, &rows, &cols, &nnz, &coo);
+    rc = smvp_load_mtx_ex(input, expand, &matcode, &rows, &cols, &nnz, &coo);
     if (rc != 0) /* mmioErrorHandler (main-cli.c:144-166) + the "only sparse" check (:1410-1414) */
         die(smvp_mmio_error_text(rc));
     printf(ANSI_COLOR_MAGENTA "[FILE]\tInput matrix file name: " ANSI_COLOR_RESET "%s\n", input);

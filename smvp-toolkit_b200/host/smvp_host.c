@@ -67,6 +67,12 @@ static char *slurp(FILE *f, size_t *len)
 
 int smvp_load_mtx(const char *path, MM_typecode *matcode, int *rows, int *cols, int64_t *nnz, smvp_coo **coo)
 {
+    return smvp_load_mtx_ex(path, 0, matcode, rows, cols, nnz, coo);
+}
+
+int smvp_load_mtx_ex(const char *path, int expand_symmetric, MM_typecode *matcode, int *rows, int *cols, int64_t *nnz,
+                     smvp_coo **coo)
+{
     FILE *f;
     int rc, nz = 0;
     char *buf, *p, *end;
@@ -111,7 +117,7 @@ int smvp_load_mtx(const char *path, MM_typecode *matcode, int *rows, int *cols, 
     fclose(f);
     if (!buf)
         return SMVP_HOST_E_ALLOC;
-    out = (smvp_coo *)malloc(sizeof(smvp_coo) * (size_t)(nz > 0 ? nz : 1));
+    out = (smvp_coo *)malloc(sizeof(smvp_coo) * (size_t)(nz > 0 ? nz : 1) * (expand_symmetric ? 2 : 1));
     if (!out)
     {
         free(buf);
@@ -150,6 +156,20 @@ int smvp_load_mtx(const char *path, MM_typecode *matcode, int *rows, int *cols, 
         return SMVP_HOST_E_ENTRIES;
     }
     *nnz = nz;
+    if (expand_symmetric && !mm_is_general(*matcode))
+    {
+        const double sign = mm_is_skew(*matcode) ? -1.0 : 1.0;
+        int64_t k = nz;
+        for (i = 0; i < nz; i++)
+            if (out[i].row != out[i].col)
+            {
+                out[k].row = out[i].col;
+                out[k].col = out[i].row;
+                out[k].val = sign * out[i].val;
+                k++;
+            }
+        *nnz = k;
+    }
     *coo = out;
     return 0;
 }

@@ -40,6 +40,16 @@ extern "C" {
  */
 int smvp_load_mtx(const char *path, MM_typecode *matcode, int *rows, int *cols, int64_t *nnz, smvp_coo **coo);
 
+/*
+ * Same, with optional expansion of the stored triangle (the reference never expands,
+ * main-cli.c:1427-1441, so its product on pwt.mtx is that of the lower triangle only):
+ * expand_symmetric != 0 appends (col,row,val) for every off-diagonal entry of a `symmetric` file and
+ * (col,row,-val) for a `skew-symmetric` one (`hermitian` real files are treated as symmetric).
+ * Off by default everywhere so that report parity with the reference is preserved.
+ */
+int smvp_load_mtx_ex(const char *path, int expand_symmetric, MM_typecode *matcode, int *rows, int *cols, int64_t *nnz,
+                     smvp_coo **coo);
+
 /* the reference's message for an mmio error code (mmioErrorHandler, main-cli.c:144-166), without colour codes */
 const char *smvp_mmio_error_text(int code);
 

@@ -262,6 +262,46 @@ def test_device_path_medium(eng, kind):
     T.free()
 
 
+def test_fanout_and_write_only_y(eng):
+    """smvp_csr_mult_device_fanout: one pass stores y into several destinations (the fused multi-GPU exchange writes
+    peers' buffers this way); every destination must equal the plain result, for both kernels."""
+    import torch
+
+    rng = np.random.default_rng(12)
+    m, n, nnz = 5000, 4000, 60000
+    coo = util.random_coo(rng, m, n, nnz)
+    x = rng.uniform(-1, 1, n)
+    y_ref = oracle.csr_mult(*oracle.csr_build(coo, m, n), x)
+    A = eng.CsrMatrix.build(coo, m, n)
+    d_x = torch.as_tensor(x, device="cuda")
+    for variant in (eng.CSR_VECTOR, eng.CSR_MERGE):
+        outs = [torch.full((m,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(3)]
+        A.mult_device_fanout(d_x, [o.data_ptr() for o in outs], variant)
+        torch.cuda.synchronize()
+        for o in outs:
+            assert util.rel_l2(o.cpu().numpy(), y_ref) <= TOL
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    with pytest.raises(eng.SmvpError):
+        A.mult_device_fanout(d_x, [outs[0].data_ptr()] * 9, eng.CSR_MERGE)  # more than 8 destinations
+    A.free()
+
+
+def test_multi_gpu_operators_if_available(eng):
+    """Row-block CSR (all exchanges) and column-block TJDS on 2 ranks, when the box has 2 GPUs."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (covered on CPU by tests/test_dist_gloo.py; run tools/check_multigpu.py on a multi-GPU box)")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29577", os.path.join(repo, "tools", "check_multigpu.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert "MULTIGPU CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 # ---------------------------------------------------------------------------- BASELINE.json full size
 def test_full_size_stencil_properties(eng):
     """Config 3 (27-point stencil 369^3, 1.35e9 nnz): size-independent properties, no oracle pass needed.

@@ -94,6 +94,40 @@ def test_loader_comments_integer_and_blank_lines(host, tmp_path):
     assert coo["row"].tolist() == [0, 2] and coo["col"].tolist() == [3, 0] and coo["val"].tolist() == [7.0, -2.0]
 
 
+def test_expand_symmetric(host, tmp_path):
+    """optional mirroring of the stored triangle (the reference never does it)."""
+    host.smvp_load_mtx_ex.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int),
+                                      ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_void_p)]
+    host.smvp_load_mtx_ex.restype = ctypes.c_int
+
+    def load_ex(path, expand):
+        code = ctypes.create_string_buffer(4)
+        m, n, nnz, p = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64(), ctypes.c_void_p()
+        assert host.smvp_load_mtx_ex(path.encode(), expand, code, ctypes.byref(m), ctypes.byref(n), ctypes.byref(nnz),
+                                     ctypes.byref(p)) == 0
+        coo = np.frombuffer((ctypes.c_char * (16 * nnz.value)).from_address(p.value), dtype=oracle.COO_DT, count=nnz.value).copy()
+        ctypes.CDLL(None).free(p)
+        return m.value, n.value, coo
+
+    for kind, sign in (("symmetric", 1.0), ("skew-symmetric", -1.0)):
+        p = tmp_path / (kind + ".mtx")
+        diag = "" if kind == "skew-symmetric" else "2 2 5.0\n"
+        p.write_text("%%MatrixMarket matrix coordinate real " + kind + "\n3 3 " + ("3" if diag else "2") + "\n2 1 4.0\n3 1 -1.5\n" + diag)
+        m, n, plain = load_ex(str(p), 0)
+        m, n, full = load_ex(str(p), 1)
+        dense = np.zeros((3, 3))
+        dense[full["row"], full["col"]] = full["val"]
+        assert len(full) == len(plain) + 2
+        assert np.array_equal(dense, sign * dense.T) if kind == "skew-symmetric" else np.array_equal(dense, dense.T)
+        assert dense[1, 0] == 4.0 and dense[0, 1] == sign * 4.0 and dense[0, 2] == sign * -1.5
+    # general files are untouched; pwt doubles its off-diagonal entries
+    m, n, a = load_ex(util.sample_path("memplus"), 1)
+    assert len(a) == 126150
+    m, n, b = load_ex(util.sample_path("pwt"), 1)
+    m, n, c = load_ex(util.sample_path("pwt"), 0)
+    assert len(b) == 2 * len(c) - int((c["row"] == c["col"]).sum())
+
+
 @pytest.mark.parametrize("name,alg", sorted(util.GOLDEN_REPORTS))
 def test_report_writer_reproduces_golden_files(host, tmp_path, name, alg):
     """Same header, same layout, same %g formatting as generateReportText (main-cli.c:294-316): with the golden
