@@ -597,21 +597,30 @@ __global__ void __launch_bounds__(256) merge_fixup_kernel(const int32_t *__restr
     const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= num_tiles)
         return;
+    // everything the common case needs is loaded up front (independent loads: one memory round trip)
     const int32_t r = tile_row[t];
-    if (tile_row[t + 1] == r)
+    const int32_t r_next = tile_row[t + 1];
+    const int32_t r_prev = t > 0 ? tile_row[t - 1] : -1;
+    const double c_prev = t > 0 ? carry_val[t - 1] : 0.0;
+    const double h = head_val[t];
+    if (r_next == r)
         return; // no row ends in this tile
-    int32_t u = t; // carries of tiles [u, t-1] belong to row r
-    while (u > 0 && tile_row[u] == r)
-        u--;
-    if (tile_row[u + 1] != r)
-        u++;
-    double acc = head_val[t];
-    if (u < t)
+    double acc;
+    if (t == 0)
+        acc = h;
+    else if (r_prev != r)
+        acc = __dadd_rn(c_prev, h); // the row was cut once: tile t-1 carries into it
+    else
     {
+        int32_t u = t - 1; // the row spans several tiles: carries of tiles [u, t-1], in tile order
+        while (u > 0 && tile_row[u] == r)
+            u--;
+        if (tile_row[u + 1] != r)
+            u++;
         acc = carry_val[u];
         for (int32_t k = u + 1; k < t; k++)
             acc = __dadd_rn(acc, carry_val[k]);
-        acc = __dadd_rn(acc, head_val[t]);
+        acc = __dadd_rn(acc, h);
     }
     store_y<FANOUT>(y, fan, r, acc);
 }
@@ -635,7 +644,7 @@ static int pick_merge_cfg(const smvp_csr *A)
     const bool skewed = A->max_row_nnz > 64.0 * (mean + 1.0);
     if (skewed || mean < 20.0)
         return 1; // 10 items per thread
-    return 0;     // 14 items per thread: two lanes per 27-point-stencil row
+    return 2;     // 14 items per thread (two lanes per 27-point-stencil row), 4 warps per CTA
 }
 
 static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)

@@ -246,10 +246,14 @@ class RowBlockCsr:
                 # write-only view of y: one store here lands in every rank's y_full
                 self.y_write = int(self.symm.multicast_ptr) + 8 * self.r0
             elif exchange in ("copy", "pipeline"):
-                self.peer_views = [self.symm.get_buffer(k, (self.nbuf * self.M,), torch.float64) for k in range(world)
-                                   if k != rank]
-                # one copy stream per peer: the copy engines work on all peers at once
-                self.copy_streams = [torch.cuda.Stream() for _ in self.peer_views]
+                # peers in ring order (rank+1, rank+2, ...): at any moment every GPU receives from one sender only
+                ring = [(rank + j) % world for j in range(1, world)]
+                self.peer_views = [self.symm.get_buffer(k, (self.nbuf * self.M,), torch.float64) for k in ring]
+                # SMVP_COPY_STREAMS=1: one stream, the ring steps follow each other (a permutation per step);
+                # default: one stream per peer, all copies in flight at once
+                nstreams = int(os.environ.get("SMVP_COPY_STREAMS", "0")) or len(self.peer_views)
+                pool = [torch.cuda.Stream() for _ in range(min(nstreams, len(self.peer_views)))]
+                self.copy_streams = [pool[i % len(pool)] for i in range(len(self.peer_views))]
                 self.copy_stream = self.copy_streams[0]
                 self.sub_events = [[torch.cuda.Event() for _ in self.subs] for _ in range(self.nbuf)]
                 self.copy_done = [[torch.cuda.Event() for _ in self.copy_streams] for _ in range(self.nbuf)]
