@@ -329,7 +329,10 @@ def run_ours(args):
     local_bytes = op.local_bytes_per_mult
     achieved = local_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": op.measured_traffic_bytes(), "kernel": op.kernel_name, "kernel_ms": kern_ms,
+                # ncu capture of THIS configuration only (N=1, stencil 369^3): profiles/traffic.json
+                "traffic": (op.measured_traffic_bytes() if (world == 1 and args.workload == "stencil27" and args.grid == 369)
+                            else None),
+                "kernel": op.kernel_name, "kernel_ms": kern_ms,
                 "algorithmic_bytes_per_launch": local_bytes, "peak_source": peak_src,
                 "frac_of_nominal_8000": achieved / 8000.0}
 

@@ -356,8 +356,19 @@ extern "C" int smvp_tjds_mult_device(smvp_tjds *A, double *d_y, int variant, int
     {
         SMVP_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double) * (size_t)A->rows, s));
         if (blocks > 0 && lim > 0)
-            SMVP_LAUNCH(tjds_atomic_kernel<4>, blocks, 256, 0, s, (const int2 *)A->seg_blocks, (const int32_t *)A->start_pos, (const int32_t *)A->slot_len,
+        {
+            const char *ue = getenv("SMVP_TJDS_UNROLL"); // tuning hook; 4 is the measured default
+            const int unroll = ue && ue[0] ? atoi(ue) : 4;
+            if (unroll == 8)
+                SMVP_LAUNCH(tjds_atomic_kernel<8>, blocks, 256, 0, s, (const int2 *)A->seg_blocks, (const int32_t *)A->start_pos, (const int32_t *)A->slot_len,
                         (const int32_t *)A->row_ind, (const double *)A->val, (const double *)A->x_perm, d_y, A->nslots, lim);
+            else if (unroll == 2)
+                SMVP_LAUNCH(tjds_atomic_kernel<2>, blocks, 256, 0, s, (const int2 *)A->seg_blocks, (const int32_t *)A->start_pos, (const int32_t *)A->slot_len,
+                        (const int32_t *)A->row_ind, (const double *)A->val, (const double *)A->x_perm, d_y, A->nslots, lim);
+            else
+                SMVP_LAUNCH(tjds_atomic_kernel<4>, blocks, 256, 0, s, (const int2 *)A->seg_blocks, (const int32_t *)A->start_pos, (const int32_t *)A->slot_len,
+                        (const int32_t *)A->row_ind, (const double *)A->val, (const double *)A->x_perm, d_y, A->nslots, lim);
+        }
     }
     else
     {
