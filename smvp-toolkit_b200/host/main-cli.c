@@ -7,9 +7,9 @@
  *
  *   -a, --all-algs        enable all SMVP algorithms (CSR then TJDS)
  *   -c, --csr             enable CSR            -t, --tjds   enable TJDS
- *   -g, --cisr-gen        (FPGA .coe emitter of the reference; not part of the GPU path: reported, skipped)
+ *   -g, --cisr-gen        generate the CISR .coe image on stdout (host-side packing, smvp_cisr.c)
  *   -n, --number=INT      iterations per algorithm (default 1000)
- *   -s, --slots=INT       CISR slots (accepted for compatibility)
+ *   -s, --slots=INT       CISR slots (default 16)
  *   -d, --dir=FOLDER      report folder (default: current directory)
  *   <file>                Matrix Market file; options come BEFORE it (POSIXLY_CORRECT parsing, as popt's
  *                         POPT_CONTEXT_POSIXMEHARDER at main-cli.c:1254)
@@ -187,7 +187,6 @@ int main(int argc, char *argv[])
             return 1;
         }
     }
-    (void)cisr_slots;
     if (optind != argc - 1) /* exactly one positional (main-cli.c:1389-1393) */
     {
         usage(argv[0]);
@@ -274,8 +273,28 @@ int main(int argc, char *argv[])
         smvp_tjds_free(T);
     }
     if (alg_mode & ALG_CISR)
-        printf(ANSI_COLOR_YELLOW "[INFO]\tCISR COE generation (-g) is the reference's FPGA file emitter (main-cli.c:473-729); it is "
-                                 "outside the GPU SpMV path and is not built into this engine.\n" ANSI_COLOR_RESET);
+    {
+        /* smvp_cisr_coegen (main-cli.c:473-729): CSR through the engine's builder, packing on the host */
+        smvp_csr *A = NULL;
+        int32_t *row_ptr = (int32_t *)malloc(sizeof(int32_t) * ((size_t)rows + 1));
+        int32_t *col_ind = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1));
+        double *val = (double *)malloc(sizeof(double) * (size_t)(nnz > 0 ? nnz : 1));
+        if (!row_ptr || !col_ind || !val)
+            die("Out of memory.");
+        printf(ANSI_COLOR_YELLOW "[INFO]\tConverting loaded content to CISR format.\n" ANSI_COLOR_RESET);
+        rc = smvp_csr_build(coo, rows, cols, nnz, &A);
+        if (rc != SMVP_OK)
+            cuda_die("smvp_csr_build", rc);
+        rc = smvp_csr_export(A, row_ptr, col_ind, val);
+        if (rc != SMVP_OK)
+            cuda_die("smvp_csr_export", rc);
+        smvp_csr_free(A);
+        if (smvp_cisr_coe(stdout, row_ptr, col_ind, val, rows, nnz, cisr_slots) != 0)
+            die("CISR COE generation failed (slot schedule overran the matrix).");
+        free(row_ptr);
+        free(col_ind);
+        free(val);
+    }
 
     printf(ANSI_COLOR_GREEN "[STOP]\tExit smvp-toolbox v%d.%d.%d\n\n" ANSI_COLOR_RESET, SMVP_MAJOR_VER, SMVP_MINOR_VER,
            SMVP_REVISION_VER);

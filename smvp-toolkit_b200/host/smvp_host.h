@@ -63,6 +63,14 @@ int smvp_write_report(const char *input_file_name, const char *report_dir, const
                       int iters, const double *y, const smvp_time_stats_t *t, unsigned long unix_time, char *out_path,
                       size_t out_path_len);
 
+/*
+ * The reference's `-g` option (smvp_cisr_coegen, main-cli.c:473-729): CSR -> CISR slot schedule -> 36-bit
+ * words of a Xilinx block-RAM .coe image, written to `out` (the reference prints to stdout).  Host-only.
+ * Returns 0, -1 on bad arguments / allocation failure, -2 where the reference aborts ("slot_group_iter overran").
+ */
+int smvp_cisr_coe(FILE *out, const int32_t *row_ptr, const int32_t *col_ind, const double *val, int rows, int64_t nnz,
+                  int slots);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,7 @@ ref_arrays.json        integer/value arrays the reference prints with its debug 
                        and TJDS perm/colLen/val/row_ind/start_pos/num_tjdiag (SMVP_TJDS_DEBUG
                        flipped to 1 in a scratch copy under /tmp, main-cli.c:11,870-992)
 random_coo.npz         the seeded random COO inputs the ref_y entries named rand* refer to
+cisr/*.coe.gz          the .coe images the reference binary prints for `-g -s <slots>` (main-cli.c:473-729)
 """
 import ctypes
 import json
@@ -159,7 +160,31 @@ def debug_arrays(tmp):
     return out
 
 
+def cisr_fixtures():
+    """.coe images printed by the UNMODIFIED reference binary for `-g -s <slots>` (smvp_cisr_coegen, main-cli.c:473-729)."""
+    import gzip
+
+    out_dir = os.path.join(HERE, "cisr")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(REPO, "oracle", "_ref", "smvp-toolkit-cli-ref")
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, slot_list in (("pdp08-pg4", (2, 4, 16, 32)), ("ibm32", (4, 16)), ("curtis54", (4, 16)), ("memplus", (16,))):
+            for slots in slot_list:
+                r = subprocess.run([exe, "-g", "-s", str(slots), "-d", tmp, os.path.join(REF, "sample-data", name + ".mtx")],
+                                   capture_output=True, text=True)
+                assert r.returncode == 0, r.stderr
+                t = r.stdout
+                a = t.index("\n;*********************************************")
+                b = t.index("03ffffffff;") + len("03ffffffff;\n\n")
+                with gzip.open(os.path.join(out_dir, "%s_s%d.coe.gz" % (name, slots)), "wt") as f:
+                    f.write(t[a:b])
+                print("cisr", name, slots, len(t[a:b].splitlines()), "lines", flush=True)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--cisr-only":
+        cisr_fixtures()
+        return
     os.makedirs(os.path.join(HERE, "sample-data"), exist_ok=True)
     os.makedirs(os.path.join(HERE, "reports"), exist_ok=True)
     for name in SAMPLES + ["badfile"]:
@@ -196,6 +221,7 @@ def main():
     with open(os.path.join(HERE, "ref_arrays.json"), "w") as f:
         json.dump(arrays, f)
     print("wrote", len(ys), "reference vectors")
+    cisr_fixtures()
 
 
 if __name__ == "__main__":

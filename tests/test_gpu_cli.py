@@ -66,3 +66,15 @@ def test_default_report_dir_is_cwd(tmp_path):
     run_cli(["-c", "-n", "2", util.sample_path("pdp08-pg4")], str(tmp_path))  # no -d: the reference crashes here (U2)
     rep = util.parse_report(glob.glob(str(tmp_path / "smvp-toolbox_report_CSR_*.txt"))[0])
     assert rep["y"].tolist() == [6, 21, 1, 7, 14, 7]
+
+
+def test_cisr_generator_option(tmp_path):
+    """`-g -s 4`: the .coe image on stdout equals the unmodified reference's (tests/golden/cisr)."""
+    import gzip
+
+    want = gzip.open(os.path.join(util.GOLDEN, "cisr", "curtis54_s4.coe.gz"), "rt").read()
+    out = run_cli(["-g", "-s", "4", util.sample_path("curtis54")], str(tmp_path))
+    a = out.index("\n;*********************************************")
+    b = out.index("03ffffffff;") + len("03ffffffff;\n\n")
+    assert out[a:b] == want
+    assert "Converting loaded content to CISR format." in out

@@ -152,6 +152,32 @@ def test_report_writer_reproduces_golden_files(host, tmp_path, name, alg):
     assert open(path).read() == golden
 
 
+@pytest.mark.parametrize("fixture", sorted(f for f in os.listdir(os.path.join(util.GOLDEN, "cisr")) if f.endswith(".coe.gz")))
+def test_cisr_coe_matches_reference_binary(host, tmp_path, fixture):
+    """`-g`: the .coe image must equal, byte for byte, what the unmodified reference prints (tests/golden/cisr)."""
+    import gzip
+
+    name, slots = fixture[: -len(".coe.gz")].rsplit("_s", 1)
+    slots = int(slots)
+    want = gzip.open(os.path.join(util.GOLDEN, "cisr", fixture), "rt").read()
+    m, n, coo = util.load_sample(name)
+    row_ptr, col_ind, val = oracle.csr_build(coo, m, n)
+    libc = ctypes.CDLL(None)
+    libc.fopen.restype = ctypes.c_void_p
+    libc.fopen.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+    libc.fclose.argtypes = [ctypes.c_void_p]
+    host.smvp_cisr_coe.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                   ctypes.c_int]
+    host.smvp_cisr_coe.restype = ctypes.c_int
+    path = str(tmp_path / "out.coe")
+    f = libc.fopen(path.encode(), b"w")
+    rc = host.smvp_cisr_coe(f, row_ptr.ctypes.data_as(ctypes.c_void_p), col_ind.ctypes.data_as(ctypes.c_void_p),
+                            val.ctypes.data_as(ctypes.c_void_p), m, len(coo), slots)
+    libc.fclose(f)
+    assert rc == 0
+    assert open(path).read() == want
+
+
 def test_cli_usage_and_option_errors():
     cli = os.path.join(LIB, "smvp-toolkit-cli")
     if not os.path.exists(cli):
