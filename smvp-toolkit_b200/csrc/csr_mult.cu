@@ -327,9 +327,10 @@ template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     csr_merge_warp_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_ind, const double *__restrict__ val,
                           const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int32_t rows,
-                          int64_t nnz, int32_t num_tiles, double *__restrict__ head_val, double *__restrict__ carry_val,
-                          const __grid_constant__ YFan fan)
+                          int64_t nnz, int32_t tile_begin, int32_t num_tiles, double *__restrict__ head_val,
+                          double *__restrict__ carry_val, const __grid_constant__ YFan fan)
 {
+    // processes tiles [tile_begin, num_tiles): a sub-range lets the host overlap the copy-out of finished rows
     static_assert(STAGES == 1, "one stage per warp: deeper rings lost to more resident warps in every sweep");
     using Shape = MergeShape<32, IPT, 1>;
     extern __shared__ __align__(128) unsigned char stage_mem[];
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             bulk_g2s(base + v.vb + v.cb, row_ptr + v.ra, v.rb, my_bar, policy);
     };
 
-    int32_t t = (int32_t)blockIdx.x * WARPS + w;
+    int32_t t = tile_begin + (int32_t)blockIdx.x * WARPS + w;
     int32_t cur_r0 = 0, cur_r1 = 0; // merge coordinates of the tile in flight: the only tile state kept across the loop
     if (t < num_tiles)
     {
@@ -616,10 +617,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 // order) + (partial of the tile where it ends).  tile_row[u+1] is the row tile u's carry belongs to.
 template <bool FANOUT>
 __global__ void __launch_bounds__(256) merge_fixup_kernel(const int32_t *__restrict__ tile_row, const double *__restrict__ head_val,
-                                                          const double *__restrict__ carry_val, int32_t num_tiles,
-                                                          double *__restrict__ y, const __grid_constant__ YFan fan)
+                                                          const double *__restrict__ carry_val, int32_t tile_begin,
+                                                          int32_t num_tiles, double *__restrict__ y,
+                                                          const __grid_constant__ YFan fan)
 {
-    const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int32_t t = tile_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= num_tiles)
         return;
     // everything the common case needs is loaded up front (independent loads: one memory round trip)
@@ -708,7 +710,8 @@ static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
     X(6, 2, 9, 1, 16)
 
 template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT>
-static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, const YFan *fanp, cudaStream_t s)
+static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, const YFan *fanp, cudaStream_t s, int32_t tile_begin,
+                         int32_t tile_end)
 {
     using Shape = MergeShape<32, IPT, STAGES>;
     constexpr int SMEM = WARPS * Shape::SMEM_BYTES;
@@ -727,15 +730,16 @@ static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, cons
         configured_dev = dev;
     }
     int64_t grid = (int64_t)device_props().sms * resident;
-    const int64_t need = ceil_div64(A->merge_tiles, WARPS);
+    const int32_t ntiles = tile_end - tile_begin;
+    const int64_t need = ceil_div64(ntiles, WARPS);
     if (grid > need)
         grid = need;
     if (grid > 0)
     {
         SMVP_LAUNCH(kern, (unsigned)grid, WARPS * 32, SMEM, s, A->row_ptr, A->col_ind, A->val, d_x, d_y, A->tile_row, A->rows,
-                    A->nnz, A->merge_tiles, A->head_val, A->carry_val, fan);
-        SMVP_LAUNCH(merge_fixup_kernel<FANOUT>, (unsigned)ceil_div64(A->merge_tiles, 256), 256, 0, s, (const int32_t *)A->tile_row,
-                    (const double *)A->head_val, (const double *)A->carry_val, A->merge_tiles, d_y, fan);
+                    A->nnz, tile_begin, tile_end, A->head_val, A->carry_val, fan);
+        SMVP_LAUNCH(merge_fixup_kernel<FANOUT>, (unsigned)ceil_div64(ntiles, 256), 256, 0, s, (const int32_t *)A->tile_row,
+                    (const double *)A->head_val, (const double *)A->carry_val, tile_begin, tile_end, d_y, fan);
     }
     return SMVP_OK;
 }
@@ -754,16 +758,20 @@ static int wmerge_tile_items(int cfg)
     }
 }
 
-static int csr_mult_merge(smvp_csr *A, const double *d_x, double *d_y, const YFan *fan, cudaStream_t s)
+// tiles [tile_begin, tile_end) of the plan; (0, -1) = all
+static int csr_mult_merge(smvp_csr *A, const double *d_x, double *d_y, const YFan *fan, cudaStream_t s, int32_t tile_begin = 0,
+                          int32_t tile_end = -1)
 {
     const int cfg = pick_merge_cfg(A);
     SMVP_TRY(merge_plan(A, cfg, s));
+    if (tile_end < 0)
+        tile_end = A->merge_tiles;
     switch (cfg)
     {
-#define X(id, wp, i, st, mb)                                                           \
-    case id:                                                                           \
-        return fan ? launch_wmerge<wp, i, st, mb, true>(A, d_x, d_y, fan, s)           \
-                   : launch_wmerge<wp, i, st, mb, false>(A, d_x, d_y, nullptr, s);
+#define X(id, wp, i, st, mb)                                                                              \
+    case id:                                                                                              \
+        return fan ? launch_wmerge<wp, i, st, mb, true>(A, d_x, d_y, fan, s, tile_begin, tile_end)        \
+                   : launch_wmerge<wp, i, st, mb, false>(A, d_x, d_y, nullptr, s, tile_begin, tile_end);
         SMVP_WMERGE_CFGS(X)
 #undef X
     default:
@@ -824,9 +832,59 @@ extern "C" int smvp_csr_mult_device_fanout(smvp_csr *A, const double *d_x, doubl
     return csr_mult_any(A, d_x, fan.p[0], &fan, variant, stream);
 }
 
+// Last pass of the host-vector entry point for large matrices: the merge-path tiles are run in a few
+// consecutive ranges and the rows a range completes are copied to the host on a second stream while the
+// next range multiplies, so most of the device->host transfer of y hides behind the SpMV.
+constexpr int CSR_OUT_CHUNKS = 8;
+
+static int csr_mult_last_overlapped(smvp_csr *A, double *y_host, cudaEvent_t e0, cudaEvent_t e1, float *ms)
+{
+    SMVP_TRY(merge_plan(A, pick_merge_cfg(A), 0));
+    const int32_t T = A->merge_tiles;
+    int32_t tb[CSR_OUT_CHUNKS + 1], rb[CSR_OUT_CHUNKS + 1];
+    for (int c = 0; c <= CSR_OUT_CHUNKS; c++)
+        tb[c] = (int32_t)((int64_t)T * c / CSR_OUT_CHUNKS);
+    for (int c = 0; c <= CSR_OUT_CHUNKS; c++) // rows consumed before each boundary tile (tile_row[T] = rows)
+        SMVP_CUDA(cudaMemcpy(&rb[c], A->tile_row + tb[c], sizeof(int32_t), cudaMemcpyDeviceToHost));
+    cudaStream_t copy_stream;
+    cudaEvent_t done[CSR_OUT_CHUNKS];
+    SMVP_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    for (int c = 0; c < CSR_OUT_CHUNKS; c++)
+        SMVP_CUDA(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
+    int rc = SMVP_OK;
+    cudaEventRecord(e0, 0);
+    for (int c = 0; c < CSR_OUT_CHUNKS && rc == SMVP_OK; c++)
+    {
+        if (tb[c + 1] > tb[c])
+            rc = csr_mult_merge(A, A->d_x, A->d_y, nullptr, 0, tb[c], tb[c + 1]);
+        cudaEventRecord(done[c], 0);
+        cudaStreamWaitEvent(copy_stream, done[c], 0);
+        if (rb[c + 1] > rb[c])
+            cudaMemcpyAsync(y_host + rb[c], A->d_y + rb[c], sizeof(double) * (size_t)(rb[c + 1] - rb[c]), cudaMemcpyDeviceToHost,
+                            copy_stream);
+    }
+    cudaEventRecord(e1, 0);
+    cudaError_t e = cudaStreamSynchronize(copy_stream);
+    if (e == cudaSuccess)
+        e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess)
+        cudaEventElapsedTime(ms, e0, e1);
+    for (int c = 0; c < CSR_OUT_CHUNKS; c++)
+        cudaEventDestroy(done[c]);
+    cudaStreamDestroy(copy_stream);
+    if (rc != SMVP_OK)
+        return rc;
+    if (e != cudaSuccess)
+        return cuda_fail(e, "overlapped copy-out", __FILE__, __LINE__);
+    SMVP_CUDA(cudaGetLastError());
+    return SMVP_OK;
+}
+
 extern "C" int smvp_csr_mult(smvp_csr *A, const double *x_host, double *y_host, int iters, double *ms_each, int variant)
 {
     if (!A || iters < 1 || (A->cols > 0 && !x_host) || (A->rows > 0 && !y_host))
+        return SMVP_E_ARG;
+    if (variant != SMVP_CSR_AUTO && variant != SMVP_CSR_VECTOR && variant != SMVP_CSR_MERGE)
         return SMVP_E_ARG;
     if (!A->d_x)
         SMVP_CUDA(dev_alloc(&A->d_x, A->cols));
@@ -838,35 +896,47 @@ extern "C" int smvp_csr_mult(smvp_csr *A, const double *x_host, double *y_host, 
     SMVP_CUDA(cudaEventCreate(&e0));
     SMVP_CUDA(cudaEventCreate(&e1));
     int rc = SMVP_OK;
+    const bool merge = csr_resolve_variant(A, variant) == SMVP_CSR_MERGE && A->rows > 0;
     // plan outside the timed bracket (the reference builds its format before the loop too)
-    if (csr_resolve_variant(A, variant) == SMVP_CSR_MERGE && A->rows > 0)
+    if (merge)
         rc = merge_plan(A, pick_merge_cfg(A), 0);
+    // big result vector: overlap its copy-out with the last pass
+    const bool overlap_out = merge && A->rows >= (1 << 20) && getenv("SMVP_NO_OVERLAP_OUT") == nullptr;
+    bool y_copied = false;
     for (int it = 0; it < iters && rc == SMVP_OK; it++)
     {
         // y is zero-filled outside the bracket (main-cli.c:405); both kernels write every row, the
         // fill only keeps the reference's structure observable
         cudaMemsetAsync(A->d_y, 0, sizeof(double) * (size_t)A->rows, 0);
-        cudaEventRecord(e0, 0);
-        rc = smvp_csr_mult_device(A, A->d_x, A->d_y, variant, nullptr);
-        cudaEventRecord(e1, 0);
-        if (rc != SMVP_OK)
-            break;
-        cudaError_t e = cudaEventSynchronize(e1);
-        if (e != cudaSuccess)
-        {
-            rc = cuda_fail(e, "cudaEventSynchronize", __FILE__, __LINE__);
-            break;
-        }
         float ms = 0.f;
-        cudaEventElapsedTime(&ms, e0, e1);
-        if (ms_each)
+        if (overlap_out && it == iters - 1)
+        {
+            rc = csr_mult_last_overlapped(A, y_host, e0, e1, &ms);
+            y_copied = rc == SMVP_OK;
+        }
+        else
+        {
+            cudaEventRecord(e0, 0);
+            rc = smvp_csr_mult_device(A, A->d_x, A->d_y, variant, nullptr);
+            cudaEventRecord(e1, 0);
+            if (rc != SMVP_OK)
+                break;
+            cudaError_t e = cudaEventSynchronize(e1);
+            if (e != cudaSuccess)
+            {
+                rc = cuda_fail(e, "cudaEventSynchronize", __FILE__, __LINE__);
+                break;
+            }
+            cudaEventElapsedTime(&ms, e0, e1);
+        }
+        if (ms_each && rc == SMVP_OK)
             ms_each[it] = (double)ms;
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (rc != SMVP_OK)
         return rc;
-    if (A->rows > 0)
+    if (A->rows > 0 && !y_copied)
         SMVP_CUDA(cudaMemcpy(y_host, A->d_y, sizeof(double) * (size_t)A->rows, cudaMemcpyDeviceToHost));
     return SMVP_OK;
 }

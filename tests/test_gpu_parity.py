@@ -262,6 +262,27 @@ def test_device_path_medium(eng, kind):
     T.free()
 
 
+def test_host_call_overlapped_copy_out(eng, monkeypatch):
+    """smvp_csr_mult on a matrix with > 2^20 rows copies y out range by range while later tile ranges still multiply;
+    the result must equal the plain path bit for bit and the oracle within 1e-12."""
+    m = n = (1 << 20) + 12345
+    r = np.arange(m, dtype=np.int64)
+    rows = np.concatenate([r, r[1:], r[:-1], r[::7]])
+    cols = np.concatenate([r, r[1:] - 1, r[:-1] + 1, (r[::7] * 31 + 5) % n])
+    key = np.unique(rows * n + cols)
+    rng = np.random.default_rng(8)
+    coo = oracle.make_coo(key // n, key % n, rng.uniform(-1, 1, len(key)))
+    x = rng.uniform(-1, 1, n)
+    y_ref = oracle.csr_mult(*oracle.csr_build(coo, m, n), x)
+    A = eng.CsrMatrix.build(coo, m, n)
+    y1, td = A.mult(x, iters=2, variant=eng.CSR_MERGE)
+    assert util.rel_l2(y1, y_ref) <= TOL and len(td.time_each) == 2 and td.time_min > 0
+    monkeypatch.setenv("SMVP_NO_OVERLAP_OUT", "1")
+    y2, _ = A.mult(x, iters=1, variant=eng.CSR_MERGE)
+    assert np.array_equal(y1.view(np.int64), y2.view(np.int64))
+    A.free()
+
+
 def test_fanout_and_write_only_y(eng):
     """smvp_csr_mult_device_fanout: one pass stores y into several destinations (the fused multi-GPU exchange writes
     peers' buffers this way); every destination must equal the plain result, for both kernels."""
