@@ -139,6 +139,31 @@ def test_skewed_rows_and_columns(eng):
     check_tjds(eng, coo, m, n, x, y_csr)
 
 
+def test_extreme_shapes(eng):
+    """A row far longer than any tile (its partial crosses thousands of warp tiles and the fix-up chain), and a
+    column far longer than a TJDS segment (one million jagged diagonals, tens of thousands of plan segments)."""
+    rng = np.random.default_rng(31)
+    # 3 x 2M, the middle row holds 1.5M entries
+    n = 2_000_000
+    c1 = np.sort(rng.choice(n, size=1_500_000, replace=False))
+    rows = np.concatenate([np.zeros(5, np.int64), np.ones(len(c1), np.int64), np.full(7, 2)])
+    cols = np.concatenate([np.arange(5) * 11, c1, np.arange(7) * 13 + 1])
+    coo = oracle.make_coo(rows, cols, rng.uniform(-1, 1, len(rows)))
+    rng.shuffle(coo)
+    x = rng.uniform(-1, 1, n)
+    y_csr = check_csr(eng, coo, 3, n, x)
+    check_tjds(eng, coo, 3, n, x, y_csr)
+    # 1M x 4, column 2 is dense (ndiag = 1M)
+    m = 1_000_000
+    rows = np.concatenate([np.arange(m), np.array([3, 999_999, 17])])
+    cols = np.concatenate([np.full(m, 2), np.array([0, 0, 3])])
+    coo = oracle.make_coo(rows, cols, rng.uniform(-1, 1, len(rows)))
+    rng.shuffle(coo)
+    x = rng.uniform(-1, 1, 4)
+    y_csr = check_csr(eng, coo, m, 4, x)
+    check_tjds(eng, coo, m, 4, x, y_csr)
+
+
 def test_out_of_range_and_bad_args(eng):
     coo = oracle.make_coo([0, 5], [0, 1], [1.0, 2.0])
     with pytest.raises(eng.SmvpError) as ei:
