@@ -51,6 +51,10 @@ int smvp_coo_histogram_device(const int32_t *d_row, const int32_t *d_col, int64_
 /* y[i] += a[i] over n doubles (fixed-order combine of partial results) */
 int smvp_vector_add_device(double *d_y, const double *d_a, int64_t n, void *stream);
 
+/* asynchronous device-to-device copy on `stream` (copy engines, no SM).  dst may be a peer mapping or an NVSwitch
+ * multicast mapping of symmetric memory: one copy to the multicast address lands in every rank's buffer. */
+int smvp_copy_device(void *d_dst, const void *d_src, int64_t bytes, void *stream);
+
 /* L2 flush helper for timing hygiene: writes `bytes` of a scratch buffer owned by the library */
 int smvp_flush_l2(int64_t bytes, void *stream);
 

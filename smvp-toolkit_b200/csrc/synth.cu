@@ -346,6 +346,15 @@ extern "C" int smvp_vector_add_device(double *d_y, const double *d_a, int64_t n,
     return SMVP_OK;
 }
 
+extern "C" int smvp_copy_device(void *d_dst, const void *d_src, int64_t bytes, void *stream)
+{
+    if (bytes < 0 || (bytes > 0 && (!d_dst || !d_src)))
+        return SMVP_E_ARG;
+    if (bytes > 0)
+        SMVP_CUDA(cudaMemcpyAsync(d_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SMVP_OK;
+}
+
 extern "C" int smvp_flush_l2(int64_t bytes, void *stream)
 {
     static thread_local void *buf = nullptr;

@@ -228,6 +228,7 @@ class RowBlockCsr:
         self.symm = None
         self.y_fan = None
         self.peer_views, self.copy_stream, self.sub_events = None, None, None
+        self.mc_base, self.y_src = None, None
         self.nbuf, self.k = 1, 0
         if world > 1 and exchange in ("multicast", "p2p", "copy", "pipeline"):
             import torch.distributed as dist
@@ -245,6 +246,19 @@ class RowBlockCsr:
                     raise RuntimeError("this system exposes no NVSwitch multicast mapping; use exchange='p2p' or 'nccl'")
                 # write-only view of y: one store here lands in every rank's y_full
                 self.y_write = int(self.symm.multicast_ptr) + 8 * self.r0
+            elif (exchange == "pipeline" and self.symm.multicast_ptr and
+                  os.environ.get("SMVP_PIPELINE_MODE", "multicast" if world >= 3 else "unicast") == "multicast"):
+                # one copy-engine transfer per step to the NVSwitch multicast address: the switch replicates my rows
+                # into every rank's y (my own included), so egress is 1/N of the vector instead of (N-1)/N.
+                # Measured on B200 (profiles/r01_multigpu.md): N=8 0.72 ms vs 0.83 ms with 7 peer copies; at N=2 the
+                # multicast copy runs at half the rate of a peer copy (1.91 vs 1.62 ms), hence the switch-over at 3.
+                self.mc_base = int(self.symm.multicast_ptr)
+                self.y_src = [torch.zeros(self.r1 - self.r0, dtype=torch.float64, device="cuda") for _ in range(self.nbuf)]
+                self.copy_streams = [torch.cuda.Stream()]
+                self.copy_stream = self.copy_streams[0]
+                self.copy_done = [[torch.cuda.Event()] for _ in range(self.nbuf)]
+                self.sub_events = [[torch.cuda.Event()] for _ in range(self.nbuf)]
+                self.copy_pending = [False] * self.nbuf
             elif exchange in ("copy", "pipeline"):
                 # peers in ring order (rank+1, rank+2, ...): at any moment every GPU receives from one sender only
                 ring = [(rank + j) % world for j in range(1, world)]
@@ -279,8 +293,11 @@ class RowBlockCsr:
                "+ device barrier",
                "copy": "pushed to every rank by the copy engines over NVLink, sub-block by sub-block, while the next "
                "sub-block's SpMV runs (%d sub-blocks) + device barrier" % len(self.subs),
-               "pipeline": "pushed to every rank by the copy engines over NVLink (%d sub-blocks, two y buffers): step k's "
-               "exchange overlaps step k+1's SpMV, the pipe is drained inside the timed region" % len(self.subs),
+               "pipeline": ("pushed to every rank by ONE copy-engine transfer per step to the NVSwitch multicast address "
+                            "(two y buffers): step k's exchange overlaps step k+1's SpMV, the pipe is drained inside the "
+                            "timed region") if self.mc_base is not None else
+               ("pushed to every rank by the copy engines over NVLink (peer copies, two y buffers): step k's "
+                "exchange overlaps step k+1's SpMV, the pipe is drained inside the timed region"),
                "none": "kept local"}[exchange if world > 1 else "none"]
         self.partition_desc = "row blocks balanced by nnz, %d ranks; x replicated; y %s" % (world, how)
         self.e2e_api = ("smvp_csr_mult(A, x_host, y_host, iters=1) [C ABI, pinned host buffers]" if world == 1 else
@@ -296,6 +313,18 @@ class RowBlockCsr:
 
         if self.y_fan is not None:
             self.A.mult_device_fanout(self.x, self.y_fan, self.variant, stream)
+        elif self.mc_base is not None:
+            main = stream if stream is not None else torch.cuda.current_stream()
+            b = self.k % self.nbuf
+            if self.copy_pending[b]:  # the copy that still reads this source buffer (two steps ago) must be done
+                main.wait_event(self.copy_done[b][0])
+            self.y_local = self.y_src[b]
+            self.y_full = self.y_sym[b * self.M:(b + 1) * self.M]
+            self.A.mult_device(self.x, self.y_local, self.variant, main)
+            self.sub_events[b][0].record(main)
+            self.copy_stream.wait_event(self.sub_events[b][0])
+            self.eng.copy_device(self.mc_base + 8 * (b * self.M + self.r0), self.y_local, 8 * (self.r1 - self.r0),
+                                 self.copy_stream)
         elif self.peer_views is not None:
             main = stream if stream is not None else torch.cuda.current_stream()
             b = self.k % self.nbuf
@@ -371,7 +400,7 @@ class RowBlockCsr:
     def free(self):
         for A in self.subs:
             A.free()
-        self.y_full = self.y_local = self.peer_views = self.y_sym = None
+        self.y_full = self.y_local = self.peer_views = self.y_sym = self.y_src = None
 
 
 class ColBlockTjds:

@@ -94,6 +94,7 @@ SIGNATURES = {
     "smvp_coo_filter_device": (_int, [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _pp, _pp, _pp, _pi64]),
     "smvp_coo_histogram_device": (_int, [_vp, _vp, _i64, _int, _i32, _vp]),
     "smvp_vector_add_device": (_int, [_vp, _vp, _i64, _vp]),
+    "smvp_copy_device": (_int, [_vp, _vp, _i64, _vp]),
     "smvp_flush_l2": (_int, [_i64, _vp]),
     "smvp_device_free": (None, [_vp]),
 }
@@ -409,6 +410,10 @@ def coo_histogram_device(d_row, d_col, nnz, by_col, nkeys, d_counts):
 
 def vector_add_device(d_y, d_a, n, stream=None):
     _check(lib().smvp_vector_add_device(_ptr(d_y), _ptr(d_a), n, _stream(stream)), "smvp_vector_add_device")
+
+
+def copy_device(d_dst, d_src, nbytes, stream=None):
+    _check(lib().smvp_copy_device(_ptr(d_dst), _ptr(d_src), nbytes, _stream(stream)), "smvp_copy_device")
 
 
 def flush_l2(nbytes=256 << 20, stream=None):

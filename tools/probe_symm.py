@@ -49,6 +49,35 @@ def main():
     local = torch.empty(per, dtype=torch.float64, device="cuda")
     remote = hdl.get_buffer(peer, (per,), torch.float64, per * rank)
     res["peer_copy_ms"] = timed(lambda: remote.copy_(local))
+    # copy-engine write to the MULTICAST address (one copy, the switch replicates it): allowed?
+    try:
+        import ctypes
+        import glob
+
+        cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*"))
+        rt = ctypes.CDLL(cands[0] if cands else "libcudart.so.12")
+        rt.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+        rt.cudaMemcpyAsync.restype = ctypes.c_int
+        src = torch.full((per,), float(rank + 1), dtype=torch.float64, device="cuda")
+        if mc:
+            def ce_mc():
+                rc = rt.cudaMemcpyAsync(ctypes.c_void_p(mc + 8 * per * rank), ctypes.c_void_p(src.data_ptr()), per * 8, 3,
+                                        ctypes.c_void_p(s.cuda_stream))
+                if rc != 0:
+                    raise RuntimeError("cudaMemcpyAsync to the multicast address failed: %d" % rc)
+            buf.zero_()
+            torch.cuda.synchronize()
+            dist.barrier()
+            ce_mc()
+            torch.cuda.synchronize()
+            hdl.barrier(channel=0)
+            torch.cuda.synchronize()
+            ok = all(bool((buf[per * k:per * (k + 1)] == float(k + 1)).all()) for k in range(world))
+            res["ce_multicast_copy_ms"] = timed(ce_mc)
+            res["ce_multicast_copy_ok"] = 1.0 if ok else 0.0
+    except Exception as e:  # noqa: BLE001
+        if rank == 0:
+            print("CE multicast probe failed:", e)
     mb = per * 8 / 1e6
     if rank == 0:
         print("block = %.1f MB per rank, world %d" % (mb, world))
