@@ -247,11 +247,12 @@ class RowBlockCsr:
                 # write-only view of y: one store here lands in every rank's y_full
                 self.y_write = int(self.symm.multicast_ptr) + 8 * self.r0
             elif (exchange == "pipeline" and self.symm.multicast_ptr and
-                  os.environ.get("SMVP_PIPELINE_MODE", "multicast" if world >= 3 else "unicast") == "multicast"):
+                  os.environ.get("SMVP_PIPELINE_MODE", "multicast" if world >= 8 else "unicast") == "multicast"):
                 # one copy-engine transfer per step to the NVSwitch multicast address: the switch replicates my rows
                 # into every rank's y (my own included), so egress is 1/N of the vector instead of (N-1)/N.
-                # Measured on B200 (profiles/r01_multigpu.md): N=8 0.72 ms vs 0.83 ms with 7 peer copies; at N=2 the
-                # multicast copy runs at half the rate of a peer copy (1.91 vs 1.62 ms), hence the switch-over at 3.
+                # Measured on B200 (profiles/r01_multigpu.md): N=8 0.72 ms vs 0.83 ms with 7 peer copies, but N=4 1.05 vs
+                # 0.85 ms and N=2 1.91 vs 1.62 ms (a multicast copy moves data at about half the rate of a peer copy),
+                # hence the switch-over at 8 ranks.
                 self.mc_base = int(self.symm.multicast_ptr)
                 self.y_src = [torch.zeros(self.r1 - self.r0, dtype=torch.float64, device="cuda") for _ in range(self.nbuf)]
                 self.copy_streams = [torch.cuda.Stream()]
