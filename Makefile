@@ -14,7 +14,7 @@ CFLAGS    := -O2 -std=gnu11 -Wall -Wextra -D_XOPEN_SOURCE=700 -Iinclude -I$(PKG)
 
 CU_SRCS   := $(wildcard $(PKG)/csrc/*.cu)
 CU_OBJS   := $(patsubst $(PKG)/csrc/%.cu,$(OBJ)/%.o,$(CU_SRCS))
-HOST_LIB  := $(PKG)/host/mmio.c $(PKG)/host/smvp_host.c
+HOST_LIB  := $(PKG)/host/smvp_mmio.c $(PKG)/host/smvp_host.c
 
 .PHONY: all oracle test clean
 all: $(LIB)/libsmvp_cuda.so $(LIB)/libsmvp_host.so $(LIB)/smvp-toolkit-cli
@@ -26,7 +26,7 @@ $(OBJ)/%.o: $(PKG)/csrc/%.cu $(PKG)/csrc/common.cuh include/smvp_cuda.h include/
 $(LIB)/libsmvp_cuda.so: $(CU_OBJS)
 	$(NVCC) -shared $(ARCH) -o $@ $^
 
-$(LIB)/libsmvp_host.so: $(HOST_LIB) $(PKG)/host/mmio.h $(PKG)/host/smvp_host.h
+$(LIB)/libsmvp_host.so: $(HOST_LIB) $(PKG)/host/smvp_mmio.h $(PKG)/host/smvp_host.h
 	@mkdir -p $(LIB)
 	$(CC) $(CFLAGS) -fPIC -shared -o $@ $(HOST_LIB) -lm
 

@@ -12,7 +12,7 @@
 #include <stddef.h>
 #include <stdint.h>
 
-#include "mmio.h"
+#include "smvp_mmio.h"
 #include "smvp_cuda.h"
 
 #ifdef __cplusplus
@@ -23,7 +23,7 @@ extern "C" {
 #define SMVP_MINOR_VER 6
 #define SMVP_REVISION_VER 4
 
-/* loader errors beyond the MM_* codes of mmio.h */
+/* loader errors beyond the MM_* codes of smvp_mmio.h */
 #define SMVP_HOST_E_OPEN 101      /* fopen failed                                                      */
 #define SMVP_HOST_E_NOT_SPARSE 102 /* array (dense) file: "only supports sparse matricies" (:1410-1414) */
 #define SMVP_HOST_E_COMPLEX 103   /* complex field: the reference mis-parses these (U15); rejected      */

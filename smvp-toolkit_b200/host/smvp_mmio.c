@@ -1,5 +1,5 @@
 /*
- * mmio.c -- see mmio.h.  Banner and size-line parsing per the Matrix Market exchange format:
+ * smvp_mmio.c -- see smvp_mmio.h.  Banner and size-line parsing per the Matrix Market exchange format:
  *   line 1:  %%MatrixMarket <object> <format> <field> <symmetry>      (case-insensitive after the tag)
  *   then any number of lines starting with '%', optional blank lines, then "rows cols nnz".
  * Behaviour the reference relies on (and tests/test_host.py pins): an empty file yields
@@ -7,7 +7,7 @@
  * with fewer than five tokens yields MM_PREMATURE_EOF, a wrong tag MM_NO_HEADER, unknown words
  * MM_UNSUPPORTED_TYPE.
  */
-#include "mmio.h"
+#include "smvp_mmio.h"
 
 #include <ctype.h>
 #include <string.h>

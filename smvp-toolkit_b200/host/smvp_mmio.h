@@ -1,14 +1,14 @@
 /*
- * mmio.h -- Matrix Market banner / size-line reader with the interface of the NIST "mmio" library the
+ * smvp_mmio.h -- Matrix Market banner / size-line reader with the interface of the NIST "mmio" library the
  * reference links (reference: mmio/mmio.h; used at main-cli.c:1405 mm_read_banner, :1419
  * mm_read_mtx_crd_size and through the mm_is_* predicates at :1410, :1429).
  *
  * Same names, same typecode convention (4 characters: object, format, field, symmetry), same error
  * codes, so host code written against the NIST header compiles against this one.  The implementation
- * (mmio.c) is written from the Matrix Market exchange-format specification, not from the NIST source.
+ * (smvp_mmio.c) is written from the Matrix Market exchange-format specification, not from the NIST source.
  */
-#ifndef SMVP_HOST_MMIO_H
-#define SMVP_HOST_MMIO_H
+#ifndef SMVP_MMIO_H
+#define SMVP_MMIO_H
 
 #include <stdio.h>
 
