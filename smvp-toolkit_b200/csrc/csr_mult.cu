@@ -165,7 +165,11 @@ __device__ __forceinline__ void store_y(double *__restrict__ y, const YFan &fan,
 }
 
 // =====================================================================================  VECTOR
-template <int LPR, bool FANOUT>
+// WIDE = true : each lane pulls 4 consecutive entries per step with 128-bit loads (long rows).
+// WIDE = false: lane l takes entries l, l+LPR, ... with 8/4-byte loads (short rows).  With only a few rows per warp
+//               the lanes of one request then sit on consecutive entries of consecutive rows, so the x gather of a
+//               banded matrix touches far fewer sectors per request -- the vector kernel is L1-bound on such rows.
+template <int LPR, bool FANOUT, bool WIDE>
 __global__ void __launch_bounds__(256) csr_vector_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_ind,
                                                          const double *__restrict__ val, const double *__restrict__ x,
                                                          double *__restrict__ y, int32_t rows, const __grid_constant__ YFan fan)
@@ -174,7 +178,23 @@ __global__ void __launch_bounds__(256) csr_vector_kernel(const int32_t *__restri
     const int64_t row = gt / LPR;
     const int lane = (int)(gt % LPR);
     double sum = 0.0;
-    if (row < rows)
+    if (row < rows && !WIDE)
+    {
+        const int32_t start = row_ptr[row], end = row_ptr[row + 1];
+        int32_t j = start + lane;
+        // two steps per trip: 4 independent loads and 2 gathers in flight per lane
+        for (; j + LPR < end; j += 2 * LPR)
+        {
+            const int32_t c0 = __ldg(col_ind + j), c1 = __ldg(col_ind + j + LPR);
+            const double v0 = __ldg(val + j), v1 = __ldg(val + j + LPR);
+            const double x0 = __ldg(x + c0), x1 = __ldg(x + c1);
+            sum = __dadd_rn(sum, __dmul_rn(v0, x0));
+            sum = __dadd_rn(sum, __dmul_rn(v1, x1));
+        }
+        if (j < end)
+            sum = __dadd_rn(sum, __dmul_rn(__ldg(val + j), __ldg(x + __ldg(col_ind + j))));
+    }
+    if (row < rows && WIDE)
     {
         const int32_t start = row_ptr[row], end = row_ptr[row + 1];
         for (int32_t j = (start & ~3) + 4 * lane; j < end; j += 4 * LPR)
@@ -219,12 +239,26 @@ static int launch_vector(const smvp_csr *A, const double *d_x, double *d_y, cons
         return SMVP_E_TOOBIG;
     if (blocks > 0)
     {
+        const char *we = getenv("SMVP_VECTOR_WIDE"); // tuning hook: force 128-bit (1) or lane-contiguous (0) loads
+        const bool wide = we && we[0] ? we[0] == '1' : LPR >= 16;
         if (fan)
-            SMVP_LAUNCH((csr_vector_kernel<LPR, true>), (unsigned)blocks, 256, 0, s, A->row_ptr, A->col_ind, A->val, d_x, d_y,
-                        A->rows, *fan);
+        {
+            if (wide)
+                SMVP_LAUNCH((csr_vector_kernel<LPR, true, true>), (unsigned)blocks, 256, 0, s, A->row_ptr, A->col_ind, A->val, d_x,
+                            d_y, A->rows, *fan);
+            else
+                SMVP_LAUNCH((csr_vector_kernel<LPR, true, false>), (unsigned)blocks, 256, 0, s, A->row_ptr, A->col_ind, A->val, d_x,
+                            d_y, A->rows, *fan);
+        }
         else
-            SMVP_LAUNCH((csr_vector_kernel<LPR, false>), (unsigned)blocks, 256, 0, s, A->row_ptr, A->col_ind, A->val, d_x, d_y,
-                        A->rows, YFan());
+        {
+            if (wide)
+                SMVP_LAUNCH((csr_vector_kernel<LPR, false, true>), (unsigned)blocks, 256, 0, s, A->row_ptr, A->col_ind, A->val, d_x,
+                            d_y, A->rows, YFan());
+            else
+                SMVP_LAUNCH((csr_vector_kernel<LPR, false, false>), (unsigned)blocks, 256, 0, s, A->row_ptr, A->col_ind, A->val, d_x,
+                            d_y, A->rows, YFan());
+        }
     }
     return SMVP_OK;
 }
