@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(256) tjds_det_kernel(const int2 *__restrict__ 
                                                        const int32_t *__restrict__ slot_len, const int32_t *__restrict__ row_ind,
                                                        const double *__restrict__ val, const double *__restrict__ x_perm,
                                                        const int32_t *__restrict__ row_exp, const int32_t *__restrict__ x_exp,
-                                                       unsigned long long *__restrict__ acc, int32_t nslots, int32_t diag_limit)
+                                                       unsigned long long *__restrict__ acc, int32_t rows, int32_t nslots,
+                                                       int32_t diag_limit)
 {
     const int2 blk = __ldg(blocks + blockIdx.x);
     const int32_t p = blk.y + threadIdx.x;
@@ -225,9 +226,9 @@ __global__ void __launch_bounds__(256) tjds_det_kernel(const int2 *__restrict__ 
                 long long hi, lo;
                 fixed_split(__dmul_rn(v[u], xp), __ldg(row_exp + r[u]) + ex, &hi, &lo);
                 if (hi != 0)
-                    atomicAdd(acc + 2 * (int64_t)r[u], (unsigned long long)hi);
+                    atomicAdd(acc + r[u], (unsigned long long)hi); // hi words [0, rows), lo words [rows, 2 rows):
                 if (lo != 0)
-                    atomicAdd(acc + 2 * (int64_t)r[u] + 1, (unsigned long long)lo);
+                    atomicAdd(acc + (int64_t)rows + r[u], (unsigned long long)lo); // a warp's reductions stay contiguous
             }
         }
     }
@@ -239,7 +240,9 @@ __global__ void __launch_bounds__(256) tjds_det_finalize_kernel(const long long 
     const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows)
         return;
-    const longlong2 a = *reinterpret_cast<const longlong2 *>(acc + 2 * (int64_t)r);
+    longlong2 a;
+    a.x = acc[r];
+    a.y = acc[(int64_t)rows + r];
     double out = 0.0;
     if (a.x != 0 || a.y != 0)
     {
@@ -377,7 +380,7 @@ extern "C" int smvp_tjds_mult_device(smvp_tjds *A, double *d_y, int variant, int
         if (blocks > 0 && lim > 0)
             SMVP_LAUNCH(tjds_det_kernel<4>, blocks, 256, 0, s, (const int2 *)A->seg_blocks, (const int32_t *)A->start_pos, (const int32_t *)A->slot_len,
                         (const int32_t *)A->row_ind, (const double *)A->val, (const double *)A->x_perm, (const int32_t *)A->row_exp,
-                        (const int32_t *)A->x_exp, (unsigned long long *)A->acc, A->nslots, lim);
+                        (const int32_t *)A->x_exp, (unsigned long long *)A->acc, A->rows, A->nslots, lim);
         SMVP_LAUNCH(tjds_det_finalize_kernel, (unsigned)ceil_div64(A->rows, 256), 256, 0, s, (const long long *)A->acc,
                     (const int32_t *)A->row_exp, (const int32_t *)A->x_exp, A->rows, d_y);
     }
