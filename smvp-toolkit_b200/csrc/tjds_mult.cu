@@ -24,6 +24,32 @@
 namespace smvp
 {
 
+// SMVP_TJDS_STREAM=1 reads the matrix streams with ld.global.nc.L1::no_allocate; measured on B200 it LOSES to
+// plain __ldg (atomic 3.19 vs 3.12 ms, deterministic 4.12 vs 3.83 ms on the 369^3 stencil), so it stays off
+#ifndef SMVP_TJDS_STREAM
+#define SMVP_TJDS_STREAM 0
+#endif
+__device__ __forceinline__ int32_t ld_stream_i32(const int32_t *p)
+{
+#if SMVP_TJDS_STREAM
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ double ld_stream_f64(const double *p)
+{
+#if SMVP_TJDS_STREAM
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 constexpr int TJDS_W = 32;           // bits kept in the low word
 constexpr int TJDS_FRAC = 62 + TJDS_W; // value = V * 2^(T_r - TJDS_FRAC), |sum V| < 2^TJDS_FRAC
 
@@ -99,8 +125,8 @@ __global__ void __launch_bounds__(256) tjds_atomic_kernel(const int2 *__restrict
         for (int u = 0; u < UNROLL; u++)
         {
             const int64_t j = (int64_t)__ldg(start_pos + d + u) + p;
-            r[u] = __ldg(row_ind + j);
-            v[u] = __ldg(val + j);
+            r[u] = ld_stream_i32(row_ind + j);
+            v[u] = ld_stream_f64(val + j);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; u++)
@@ -109,7 +135,7 @@ __global__ void __launch_bounds__(256) tjds_atomic_kernel(const int2 *__restrict
     for (; d < len; d++)
     {
         const int64_t j = (int64_t)__ldg(start_pos + d) + p;
-        atomicAdd(y + __ldg(row_ind + j), __dmul_rn(__ldg(val + j), xp));
+        atomicAdd(y + ld_stream_i32(row_ind + j), __dmul_rn(ld_stream_f64(val + j), xp));
     }
 }
 
@@ -214,8 +240,8 @@ __global__ void __launch_bounds__(256) tjds_det_kernel(const int2 *__restrict__ 
             if (d0 + u < len)
             {
                 const int64_t j = (int64_t)__ldg(start_pos + d0 + u) + p;
-                r[u] = __ldg(row_ind + j);
-                v[u] = __ldg(val + j);
+                r[u] = ld_stream_i32(row_ind + j);
+                v[u] = ld_stream_f64(val + j);
             }
         }
 #pragma unroll
