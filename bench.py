@@ -355,9 +355,9 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t[0]) / e2e_steps
+        # whole-job bytes per step: x crosses PCIe once (each rank uploads its slice), y comes back once
         e2e = {"value": nbytes / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(N * 8),
-               "d2h_bytes_per_step": int(op.local_rows_out * 8), "ms_per_step": e2e_ms, "steps": e2e_steps,
-               "api": op.e2e_api}
+               "d2h_bytes_per_step": int(M * 8), "ms_per_step": e2e_ms, "steps": e2e_steps, "api": op.e2e_api}
         del hx, hy
 
     clocks = sampler.result()
