@@ -55,6 +55,10 @@ int smvp_vector_add_device(double *d_y, const double *d_a, int64_t n, void *stre
  * multicast mapping of symmetric memory: one copy to the multicast address lands in every rank's buffer. */
 int smvp_copy_device(void *d_dst, const void *d_src, int64_t bytes, void *stream);
 
+/* the same copy done by a small SM kernel (`ctas` CTAs, 128-bit loads and stores) instead of the copy engines: useful
+ * when dst is a multicast mapping, where coalesced SM stores move data faster than a copy-engine transfer */
+int smvp_push_device(void *d_dst, const void *d_src, int64_t bytes, int ctas, void *stream);
+
 /* L2 flush helper for timing hygiene: writes `bytes` of a scratch buffer owned by the library */
 int smvp_flush_l2(int64_t bytes, void *stream);
 

@@ -165,6 +165,15 @@ __global__ void __launch_bounds__(256) vector_add_kernel(double *__restrict__ y,
         y[i] = __dadd_rn(y[i], a[i]);
 }
 
+__global__ void __launch_bounds__(512) push_kernel(double2 *__restrict__ dst, const double2 *__restrict__ src, int64_t n16,
+                                                   double *__restrict__ dst_tail, const double *__restrict__ src_tail, int tail)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+    if (blockIdx.x == 0 && (int)threadIdx.x < tail)
+        dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+
 static inline unsigned grid_for(int64_t n, int per_thread = 4)
 {
     int64_t blocks = ceil_div64(n > 0 ? n : 1, 256 * per_thread);
@@ -352,6 +361,31 @@ extern "C" int smvp_copy_device(void *d_dst, const void *d_src, int64_t bytes, v
         return SMVP_E_ARG;
     if (bytes > 0)
         SMVP_CUDA(cudaMemcpyAsync(d_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return SMVP_OK;
+}
+
+extern "C" int smvp_push_device(void *d_dst, const void *d_src, int64_t bytes, int ctas, void *stream)
+{
+    if (bytes < 0 || ctas < 1 || (bytes % 8) != 0 || (bytes > 0 && (!d_dst || !d_src)))
+        return SMVP_E_ARG;
+    if (bytes == 0)
+        return SMVP_OK;
+    // 16-byte vectors need both pointers 16-byte aligned; otherwise peel one double in front
+    char *dst = (char *)d_dst;
+    const char *src = (const char *)d_src;
+    if ((((uintptr_t)dst) & 15) != (((uintptr_t)src) & 15))
+        return smvp_copy_device(d_dst, d_src, bytes, stream); // mutually misaligned: let the copy engines do it
+    int64_t head = (((uintptr_t)dst) & 15) ? 8 : 0;
+    if (head > bytes)
+        head = bytes;
+    if (head)
+        SMVP_CUDA(cudaMemcpyAsync(dst, src, (size_t)head, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    const int64_t body = bytes - head;
+    const int64_t n16 = body / 16;
+    const int tail = (int)((body % 16) / 8);
+    SMVP_LAUNCH(push_kernel, (unsigned)ctas, 512, 0, (cudaStream_t)stream, (double2 *)(dst + head), (const double2 *)(src + head), n16,
+                (double *)(dst + head + 16 * n16), (const double *)(src + head + 16 * n16), tail);
+    SMVP_CUDA(cudaGetLastError());
     return SMVP_OK;
 }
 

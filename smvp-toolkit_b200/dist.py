@@ -255,7 +255,11 @@ class RowBlockCsr:
                 # hence the switch-over at 8 ranks.
                 self.mc_base = int(self.symm.multicast_ptr)
                 self.y_src = [torch.zeros(self.r1 - self.r0, dtype=torch.float64, device="cuda") for _ in range(self.nbuf)]
-                self.copy_streams = [torch.cuda.Stream()]
+                # the push is done by a small high-priority SM kernel (SMVP_PUSH_CTAS CTAs, 128-bit stores) rather than
+                # the copy engines: measured at 8 ranks 0.661 ms/step with 32 CTAs vs 0.708 ms with a copy-engine transfer
+                # (gpurun_out bench_n8_push32.json / bench_n8_final.json).  SMVP_PUSH_CTAS=0 selects the copy engines.
+                self.push_ctas = int(os.environ.get("SMVP_PUSH_CTAS", "32"))
+                self.copy_streams = [torch.cuda.Stream(priority=-1) if self.push_ctas > 0 else torch.cuda.Stream()]
                 self.copy_stream = self.copy_streams[0]
                 self.copy_done = [[torch.cuda.Event()] for _ in range(self.nbuf)]
                 self.sub_events = [[torch.cuda.Event()] for _ in range(self.nbuf)]
@@ -294,9 +298,11 @@ class RowBlockCsr:
                "+ device barrier",
                "copy": "pushed to every rank by the copy engines over NVLink, sub-block by sub-block, while the next "
                "sub-block's SpMV runs (%d sub-blocks) + device barrier" % len(self.subs),
-               "pipeline": ("pushed to every rank by ONE copy-engine transfer per step to the NVSwitch multicast address "
+               "pipeline": ("pushed to every rank by ONE %s per step to the NVSwitch multicast address "
                             "(two y buffers): step k's exchange overlaps step k+1's SpMV, the pipe is drained inside the "
-                            "timed region") if self.mc_base is not None else
+                            "timed region" % ("small SM copy kernel (%d CTAs)" % self.push_ctas
+                                              if getattr(self, "push_ctas", 0) > 0 else "copy-engine transfer"))
+               if self.mc_base is not None else
                ("pushed to every rank by the copy engines over NVLink (peer copies, two y buffers): step k's "
                 "exchange overlaps step k+1's SpMV, the pipe is drained inside the timed region"),
                "none": "kept local"}[exchange if world > 1 else "none"]
@@ -325,8 +331,12 @@ class RowBlockCsr:
             self.A.mult_device(self.x, self.y_local, self.variant, main)
             self.sub_events[b][0].record(main)
             self.copy_stream.wait_event(self.sub_events[b][0])
-            self.eng.copy_device(self.mc_base + 8 * (b * self.M + self.r0), self.y_local, 8 * (self.r1 - self.r0),
-                                 self.copy_stream)
+            if self.push_ctas > 0:
+                self.eng.push_device(self.mc_base + 8 * (b * self.M + self.r0), self.y_local, 8 * (self.r1 - self.r0),
+                                     self.push_ctas, self.copy_stream)
+            else:
+                self.eng.copy_device(self.mc_base + 8 * (b * self.M + self.r0), self.y_local, 8 * (self.r1 - self.r0),
+                                     self.copy_stream)
         elif self.peer_views is not None:
             main = stream if stream is not None else torch.cuda.current_stream()
             b = self.k % self.nbuf

@@ -95,6 +95,7 @@ SIGNATURES = {
     "smvp_coo_histogram_device": (_int, [_vp, _vp, _i64, _int, _i32, _vp]),
     "smvp_vector_add_device": (_int, [_vp, _vp, _i64, _vp]),
     "smvp_copy_device": (_int, [_vp, _vp, _i64, _vp]),
+    "smvp_push_device": (_int, [_vp, _vp, _i64, _int, _vp]),
     "smvp_flush_l2": (_int, [_i64, _vp]),
     "smvp_device_free": (None, [_vp]),
 }
@@ -414,6 +415,10 @@ def vector_add_device(d_y, d_a, n, stream=None):
 
 def copy_device(d_dst, d_src, nbytes, stream=None):
     _check(lib().smvp_copy_device(_ptr(d_dst), _ptr(d_src), nbytes, _stream(stream)), "smvp_copy_device")
+
+
+def push_device(d_dst, d_src, nbytes, ctas=16, stream=None):
+    _check(lib().smvp_push_device(_ptr(d_dst), _ptr(d_src), nbytes, ctas, _stream(stream)), "smvp_push_device")
 
 
 def flush_l2(nbytes=256 << 20, stream=None):
