@@ -103,7 +103,15 @@ int smvp_csr_build_device(const int32_t *d_row, const int32_t *d_col, const doub
                           int32_t cols, int64_t nnz, smvp_csr **out); /* synchronous */
 int smvp_tjds_build_device(const int32_t *d_row, const int32_t *d_col, const double *d_val, int32_t rows,
                            int32_t cols, int64_t nnz, smvp_tjds **out); /* synchronous */
-/* one pass y = A x */
+/* Declares the x of the following passes (the reference multiplies the SAME x `-n` times, main-cli.c:368-369 /
+ * :402-420).  Handles whose multiply plan relabels the column space by popularity (power-law matrices whose x
+ * exceeds L2, see smvp_csr_info_t.x_relabel) form their permuted copy of x here, once, the way the reference
+ * permutes x once for TJDS (main-cli.c:907-923); for all other handles the call only records the pointer.
+ * d_x stays owned by the caller and must remain valid and unchanged while passes with d_x == NULL run.
+ * The first call on a handle may synchronise (it decides and builds the plan).                              */
+int smvp_csr_set_x_device(smvp_csr *A, const double *d_x, void *stream);
+/* one pass y = A x.  d_x == NULL: the x last given to smvp_csr_set_x_device.  d_x != NULL is always
+ * correct too; on a relabelled handle it costs one extra permutation pass over x per call.             */
 int smvp_csr_mult_device(smvp_csr *A, const double *d_x, double *d_y, int variant, void *stream);
 /* one pass y = A x with the result stored into n_out (<= 8) destinations at once: d_y_list[k][r] = y[r] for
  * every row r of A and every k.  The destinations may be peer-mapped buffers of other GPUs (NVLink symmetric
@@ -127,6 +135,9 @@ typedef struct smvp_csr_info_t
     int64_t bytes_per_mult;   /* algorithmic bytes of one pass: 12 nnz + 4 (rows+1) + 8 cols + 8 rows */
     int64_t device_bytes;     /* HBM held by the handle                                        */
     int32_t launches_per_mult[3]; /* kernels one pass launches, indexed by variant (0 = AUTO)   */
+    int32_t x_relabel;        /* multiply plan: 1 = the kernels read popularity-relabelled column indices
+                                 and a permuted copy of x (row sums keep their order: y is bit-identical),
+                                 -1 = natural order kept, 0 = not decided yet (decided at the first pass) */
 } smvp_csr_info_t;
 
 typedef struct smvp_tjds_info_t

@@ -122,7 +122,25 @@ struct smvp_csr
     double *carry_val;      // [merge_tiles] partial of the row that continues past the tile
     // scratch for the host-vector entry point
     double *d_x, *d_y;
+    // plan of the pipelined host-vector pass (csr_mult.cu): tile ranges, the rows each completes and how much of x
+    // (a leading part, x arrives front to back) each reads.  Host-side copies; pipe_cfg = tile size they were cut for.
+    int32_t pipe_cfg;
+    int32_t pipe_tile[33], pipe_row[33], pipe_xneed[32];
+    void *pipe_res; // streams and events of that pass, created on first use (csr_mult.cu)
+    // popularity relabelling of the column space (csr_relabel.cu): 0 undecided, 1 in use, -1 not worth it
+    int32_t relabel_state;
+    int32_t *col_rel;    // [nnz]  rank of col_ind[j]; what the kernels read instead of col_ind when in use
+    int32_t *x_order;    // [cols] column with rank p
+    double *x_rel;       // [cols] x in rank order
+    const double *x_set; // the x last given to smvp_csr_set_x_device (caller-owned)
 };
+namespace smvp
+{
+void csr_pipe_release(smvp_csr *A);                                // csr_mult.cu
+int csr_relabel_plan(smvp_csr *A, cudaStream_t s);                 // csr_relabel.cu
+int csr_relabel_x(smvp_csr *A, const double *d_x, cudaStream_t s); // csr_relabel.cu
+void csr_relabel_release(smvp_csr *A);                             // csr_relabel.cu
+} // namespace smvp
 
 struct smvp_tjds
 {

@@ -37,6 +37,8 @@ static void csr_release(smvp_csr *A)
     cudaFree(A->carry_val);
     cudaFree(A->d_x);
     cudaFree(A->d_y);
+    csr_pipe_release(A);
+    csr_relabel_release(A);
     delete A;
 }
 

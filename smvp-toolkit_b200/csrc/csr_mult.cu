@@ -230,6 +230,9 @@ __global__ void __launch_bounds__(256) csr_vector_kernel(const int32_t *__restri
         store_y<FANOUT>(y, fan, row, sum);
 }
 
+// the column indices the multiply kernels read: the relabelled copy when that plan is in use (csr_relabel.cu)
+static inline const int32_t *mult_cols(const smvp_csr *A) { return A->relabel_state == 1 ? A->col_rel : A->col_ind; }
+
 template <int LPR>
 static int launch_vector(const smvp_csr *A, const double *d_x, double *d_y, const YFan *fan, cudaStream_t s)
 {
@@ -244,19 +247,19 @@ static int launch_vector(const smvp_csr *A, const double *d_x, double *d_y, cons
         if (fan)
         {
             if (wide)
-                SMVP_LAUNCH((csr_vector_kernel<LPR, true, true>), (unsigned)blocks, 256, 0, s, A->row_ptr, A->col_ind, A->val, d_x,
+                SMVP_LAUNCH((csr_vector_kernel<LPR, true, true>), (unsigned)blocks, 256, 0, s, A->row_ptr, mult_cols(A), A->val, d_x,
                             d_y, A->rows, *fan);
             else
-                SMVP_LAUNCH((csr_vector_kernel<LPR, true, false>), (unsigned)blocks, 256, 0, s, A->row_ptr, A->col_ind, A->val, d_x,
+                SMVP_LAUNCH((csr_vector_kernel<LPR, true, false>), (unsigned)blocks, 256, 0, s, A->row_ptr, mult_cols(A), A->val, d_x,
                             d_y, A->rows, *fan);
         }
         else
         {
             if (wide)
-                SMVP_LAUNCH((csr_vector_kernel<LPR, false, true>), (unsigned)blocks, 256, 0, s, A->row_ptr, A->col_ind, A->val, d_x,
+                SMVP_LAUNCH((csr_vector_kernel<LPR, false, true>), (unsigned)blocks, 256, 0, s, A->row_ptr, mult_cols(A), A->val, d_x,
                             d_y, A->rows, YFan());
             else
-                SMVP_LAUNCH((csr_vector_kernel<LPR, false, false>), (unsigned)blocks, 256, 0, s, A->row_ptr, A->col_ind, A->val, d_x,
+                SMVP_LAUNCH((csr_vector_kernel<LPR, false, false>), (unsigned)blocks, 256, 0, s, A->row_ptr, mult_cols(A), A->val, d_x,
                             d_y, A->rows, YFan());
         }
     }
@@ -770,7 +773,7 @@ static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, cons
         grid = need;
     if (grid > 0)
     {
-        SMVP_LAUNCH(kern, (unsigned)grid, WARPS * 32, SMEM, s, A->row_ptr, A->col_ind, A->val, d_x, d_y, A->tile_row, A->rows,
+        SMVP_LAUNCH(kern, (unsigned)grid, WARPS * 32, SMEM, s, A->row_ptr, mult_cols(A), A->val, d_x, d_y, A->tile_row, A->rows,
                     A->nnz, tile_begin, tile_end, A->head_val, A->carry_val, fan);
         SMVP_LAUNCH(merge_fixup_kernel<FANOUT>, (unsigned)ceil_div64(ntiles, 256), 256, 0, s, (const int32_t *)A->tile_row,
                     (const double *)A->head_val, (const double *)A->carry_val, tile_begin, tile_end, d_y, fan);
@@ -829,6 +832,17 @@ int csr_resolve_variant(const smvp_csr *A, int variant)
 
 using namespace smvp;
 
+// x is already in the space the kernels index (x itself, or x_rel when the relabelling plan is in use)
+static int csr_mult_launch(smvp_csr *A, const double *x, double *d_y, const YFan *fan, int variant, cudaStream_t s)
+{
+    const int v = csr_resolve_variant(A, variant);
+    int rc = (v == SMVP_CSR_VECTOR) ? csr_mult_vector(A, x, d_y, fan, s) : csr_mult_merge(A, x, d_y, fan, s);
+    if (rc != SMVP_OK)
+        return rc;
+    SMVP_CUDA(cudaGetLastError());
+    return SMVP_OK;
+}
+
 static int csr_mult_any(smvp_csr *A, const double *d_x, double *d_y, const YFan *fan, int variant, void *stream)
 {
     if (variant != SMVP_CSR_AUTO && variant != SMVP_CSR_VECTOR && variant != SMVP_CSR_MERGE)
@@ -836,17 +850,39 @@ static int csr_mult_any(smvp_csr *A, const double *d_x, double *d_y, const YFan 
     if (A->rows == 0)
         return SMVP_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    const int v = csr_resolve_variant(A, variant);
-    int rc = (v == SMVP_CSR_VECTOR) ? csr_mult_vector(A, d_x, d_y, fan, s) : csr_mult_merge(A, d_x, d_y, fan, s);
-    if (rc != SMVP_OK)
-        return rc;
-    SMVP_CUDA(cudaGetLastError());
+    SMVP_TRY(csr_relabel_plan(A, s));
+    const double *x = d_x; // NULL: the x last given to smvp_csr_set_x_device
+    if (A->relabel_state == 1)
+    {
+        if (d_x)
+            SMVP_TRY(csr_relabel_x(A, d_x, s));
+        else if (!A->x_set)
+            return SMVP_E_ARG;
+        x = A->x_rel;
+    }
+    else if (!d_x)
+    {
+        x = A->x_set;
+        if (!x && A->cols > 0)
+            return SMVP_E_ARG;
+    }
+    return csr_mult_launch(A, x, d_y, fan, variant, s);
+}
+
+extern "C" int smvp_csr_set_x_device(smvp_csr *A, const double *d_x, void *stream)
+{
+    if (!A || (A->cols > 0 && !d_x))
+        return SMVP_E_ARG;
+    SMVP_TRY(csr_relabel_plan(A, (cudaStream_t)stream));
+    if (A->relabel_state == 1)
+        SMVP_TRY(csr_relabel_x(A, d_x, (cudaStream_t)stream));
+    A->x_set = d_x;
     return SMVP_OK;
 }
 
 extern "C" int smvp_csr_mult_device(smvp_csr *A, const double *d_x, double *d_y, int variant, void *stream)
 {
-    if (!A || (A->cols > 0 && !d_x) || (A->rows > 0 && !d_y))
+    if (!A || (A->rows > 0 && !d_y))
         return SMVP_E_ARG;
     return csr_mult_any(A, d_x, d_y, nullptr, variant, stream);
 }
@@ -854,7 +890,7 @@ extern "C" int smvp_csr_mult_device(smvp_csr *A, const double *d_x, double *d_y,
 extern "C" int smvp_csr_mult_device_fanout(smvp_csr *A, const double *d_x, double *const *d_y_list, int n_out, int variant,
                                            void *stream)
 {
-    if (!A || (A->cols > 0 && !d_x) || !d_y_list || n_out < 1 || n_out > SMVP_MAX_FANOUT)
+    if (!A || !d_y_list || n_out < 1 || n_out > SMVP_MAX_FANOUT)
         return SMVP_E_ARG;
     YFan fan;
     fan.n = n_out;
@@ -866,50 +902,207 @@ extern "C" int smvp_csr_mult_device_fanout(smvp_csr *A, const double *d_x, doubl
     return csr_mult_any(A, d_x, fan.p[0], &fan, variant, stream);
 }
 
-// Last pass of the host-vector entry point for large matrices: the merge-path tiles are run in a few
-// consecutive ranges and the rows a range completes are copied to the host on a second stream while the
-// next range multiplies, so most of the device->host transfer of y hides behind the SpMV.
-constexpr int CSR_OUT_CHUNKS = 8;
+// ------------------------------------------------------------------ host-vector entry point
+// For large matrices the pass that touches the host is cut into PIPE_RANGES consecutive ranges of merge-path
+// tiles and pipelined against both PCIe directions:
+//   * first pass: x goes up in PIPE_XCHUNKS pieces on an upload stream; range c starts as soon as the leading
+//     part of x it reads (x[0 .. xneed_c), xneed_c = 1 + the largest column index among its nonzeros, a property
+//     of the matrix found once per handle) has arrived.  A banded matrix (stencils, meshes) therefore multiplies
+//     while x is still uploading; a matrix whose first rows reach the last column simply waits for all of x.
+//   * last pass: the rows a range completes are copied to the host on a download stream while the next range
+//     multiplies.
+// With iters == 1 both happen in the same pass and the call costs about ONE vector transfer (PCIe is full
+// duplex) instead of upload + multiply + download back to back.  ms_each still reports the multiply alone: the
+// sum of the ranges' own event brackets, each opened after the range's wait for x.
+constexpr int PIPE_RANGES = 32;
+constexpr int PIPE_XCHUNKS = 64;
 
-static int csr_mult_last_overlapped(smvp_csr *A, double *y_host, cudaEvent_t e0, cudaEvent_t e1, float *ms)
+__global__ void __launch_bounds__(256) col_max_kernel(const int32_t *__restrict__ col_ind, int64_t n0, int64_t n1,
+                                                      int32_t *__restrict__ out)
+{
+    int32_t m = -1;
+    for (int64_t j = n0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n1; j += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, __ldg(col_ind + j));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m >= 0)
+        atomicMax(out, m);
+}
+
+static int pipe_plan(smvp_csr *A)
 {
     SMVP_TRY(merge_plan(A, pick_merge_cfg(A), 0));
+    if (A->pipe_cfg == A->merge_cfg)
+        return SMVP_OK;
     const int32_t T = A->merge_tiles;
-    int32_t tb[CSR_OUT_CHUNKS + 1], rb[CSR_OUT_CHUNKS + 1];
-    for (int c = 0; c <= CSR_OUT_CHUNKS; c++)
-        tb[c] = (int32_t)((int64_t)T * c / CSR_OUT_CHUNKS);
-    for (int c = 0; c <= CSR_OUT_CHUNKS; c++) // rows consumed before each boundary tile (tile_row[T] = rows)
-        SMVP_CUDA(cudaMemcpy(&rb[c], A->tile_row + tb[c], sizeof(int32_t), cudaMemcpyDeviceToHost));
-    cudaStream_t copy_stream;
-    cudaEvent_t done[CSR_OUT_CHUNKS];
-    SMVP_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-    for (int c = 0; c < CSR_OUT_CHUNKS; c++)
-        SMVP_CUDA(cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming));
-    int rc = SMVP_OK;
-    cudaEventRecord(e0, 0);
-    for (int c = 0; c < CSR_OUT_CHUNKS && rc == SMVP_OK; c++)
+    const int64_t tile_items = A->merge_cfg;
+    int32_t *d_max = nullptr;
+    SMVP_CUDA(dev_alloc(&d_max, PIPE_RANGES));
+    cudaError_t e = cudaMemset(d_max, 0xff, sizeof(int32_t) * PIPE_RANGES); // -1: the range reads no x at all
+    for (int c = 0; c <= PIPE_RANGES && e == cudaSuccess; c++)
     {
-        if (tb[c + 1] > tb[c])
-            rc = csr_mult_merge(A, A->d_x, A->d_y, nullptr, 0, tb[c], tb[c + 1]);
-        cudaEventRecord(done[c], 0);
-        cudaStreamWaitEvent(copy_stream, done[c], 0);
-        if (rb[c + 1] > rb[c])
-            cudaMemcpyAsync(y_host + rb[c], A->d_y + rb[c], sizeof(double) * (size_t)(rb[c + 1] - rb[c]), cudaMemcpyDeviceToHost,
-                            copy_stream);
+        A->pipe_tile[c] = (int32_t)((int64_t)T * c / PIPE_RANGES);
+        // rows consumed before each boundary tile (tile_row[T] = rows)
+        e = cudaMemcpy(&A->pipe_row[c], A->tile_row + A->pipe_tile[c], sizeof(int32_t), cudaMemcpyDeviceToHost);
     }
-    cudaEventRecord(e1, 0);
-    cudaError_t e = cudaStreamSynchronize(copy_stream);
+    for (int c = 0; c < PIPE_RANGES && e == cudaSuccess; c++)
+    {
+        // nonzeros of the range: merge items before the boundary minus the row ends among them
+        int64_t n0 = (int64_t)A->pipe_tile[c] * tile_items - A->pipe_row[c];
+        int64_t n1 = (int64_t)A->pipe_tile[c + 1] * tile_items - A->pipe_row[c + 1];
+        n0 = n0 < A->nnz ? n0 : A->nnz;
+        n1 = (c + 1 == PIPE_RANGES || n1 > A->nnz) ? A->nnz : n1;
+        if (n1 > n0)
+        {
+            int64_t grid = ceil_div64(n1 - n0, 256 * 16);
+            const int64_t cap = (int64_t)device_props().sms * 8;
+            SMVP_LAUNCH(col_max_kernel, (unsigned)(grid < cap ? grid : cap), 256, 0, 0, (const int32_t *)A->col_ind, n0, n1,
+                        d_max + c);
+        }
+    }
+    int32_t h_max[PIPE_RANGES];
     if (e == cudaSuccess)
-        e = cudaEventSynchronize(e1);
+        e = cudaMemcpy(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost);
+    cudaFree(d_max);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "pipe_plan", __FILE__, __LINE__);
+    int32_t need = 0; // x arrives front to back, so a range needs everything up to the largest column seen so far
+    for (int c = 0; c < PIPE_RANGES; c++)
+    {
+        need = h_max[c] + 1 > need ? h_max[c] + 1 : need;
+        A->pipe_xneed[c] = need;
+    }
+    A->pipe_cfg = A->merge_cfg;
+    return SMVP_OK;
+}
+
+struct PipeResources
+{
+    cudaStream_t up = nullptr, down = nullptr;
+    cudaEvent_t x_ready[PIPE_XCHUNKS] = {}, done[PIPE_RANGES] = {}, t0[PIPE_RANGES] = {}, t1[PIPE_RANGES] = {};
+    cudaError_t create()
+    {
+        cudaError_t e = cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking);
+        if (e == cudaSuccess)
+            e = cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking);
+        for (int c = 0; c < PIPE_XCHUNKS && e == cudaSuccess; c++)
+            e = cudaEventCreateWithFlags(&x_ready[c], cudaEventDisableTiming);
+        for (int c = 0; c < PIPE_RANGES && e == cudaSuccess; c++)
+        {
+            e = cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming);
+            if (e == cudaSuccess)
+                e = cudaEventCreate(&t0[c]);
+            if (e == cudaSuccess)
+                e = cudaEventCreate(&t1[c]);
+        }
+        return e;
+    }
+    ~PipeResources()
+    {
+        for (int c = 0; c < PIPE_XCHUNKS; c++)
+            if (x_ready[c])
+                cudaEventDestroy(x_ready[c]);
+        for (int c = 0; c < PIPE_RANGES; c++)
+        {
+            if (done[c])
+                cudaEventDestroy(done[c]);
+            if (t0[c])
+                cudaEventDestroy(t0[c]);
+            if (t1[c])
+                cudaEventDestroy(t1[c]);
+        }
+        if (up)
+            cudaStreamDestroy(up);
+        if (down)
+            cudaStreamDestroy(down);
+    }
+};
+
+namespace smvp
+{
+void csr_pipe_release(smvp_csr *A)
+{
+    delete static_cast<PipeResources *>(A->pipe_res);
+    A->pipe_res = nullptr;
+}
+} // namespace smvp
+
+// one pass in ranges; x_host != NULL: upload x under the pass; y_host != NULL: download y under the pass
+static int csr_mult_pipelined(smvp_csr *A, const double *x_host, double *y_host, float *ms)
+{
+    SMVP_TRY(pipe_plan(A));
+    cudaError_t e = cudaSuccess;
+    if (!A->pipe_res) // streams and events live with the handle: creating ~160 events per call costs more than a range
+    {
+        PipeResources *fresh = new (std::nothrow) PipeResources();
+        if (!fresh)
+            return SMVP_E_ALLOC;
+        e = fresh->create();
+        if (e != cudaSuccess)
+        {
+            delete fresh;
+            return cuda_fail(e, "pipeline resources", __FILE__, __LINE__);
+        }
+        A->pipe_res = fresh;
+    }
+    PipeResources &R = *static_cast<PipeResources *>(A->pipe_res);
+    const int64_t xchunk = ((ceil_div64(A->cols, PIPE_XCHUNKS) + 63) / 64) * 64; // entries per upload piece (512 B multiple)
+    if (x_host)
+    {
+        for (int k = 0; k < PIPE_XCHUNKS; k++)
+        {
+            const int64_t a = (int64_t)k * xchunk, b = a + xchunk < A->cols ? a + xchunk : A->cols;
+            if (b > a)
+                cudaMemcpyAsync(A->d_x + a, x_host + a, sizeof(double) * (size_t)(b - a), cudaMemcpyHostToDevice, R.up);
+            cudaEventRecord(R.x_ready[k], R.up);
+        }
+    }
+    int rc = SMVP_OK;
+    const double *xm = A->relabel_state == 1 ? A->x_rel : A->d_x; // callers upload under the pass only without relabelling
+    int waited = -1; // last upload piece the compute stream already waits for
+    for (int c = 0; c < PIPE_RANGES && rc == SMVP_OK; c++)
+    {
+        if (x_host && A->pipe_xneed[c] > 0)
+        {
+            int k = (int)(((int64_t)A->pipe_xneed[c] - 1) / xchunk);
+            k = k < PIPE_XCHUNKS ? k : PIPE_XCHUNKS - 1;
+            if (k > waited)
+            {
+                cudaStreamWaitEvent(0, R.x_ready[k], 0); // pieces are in stream order: k implies all before it
+                waited = k;
+            }
+        }
+        cudaEventRecord(R.t0[c], 0);
+        if (A->pipe_tile[c + 1] > A->pipe_tile[c])
+            rc = csr_mult_merge(A, xm, A->d_y, nullptr, 0, A->pipe_tile[c], A->pipe_tile[c + 1]);
+        cudaEventRecord(R.t1[c], 0);
+        if (y_host)
+        {
+            cudaEventRecord(R.done[c], 0);
+            cudaStreamWaitEvent(R.down, R.done[c], 0);
+            const int32_t r0 = A->pipe_row[c], r1 = A->pipe_row[c + 1];
+            if (r1 > r0)
+                cudaMemcpyAsync(y_host + r0, A->d_y + r0, sizeof(double) * (size_t)(r1 - r0), cudaMemcpyDeviceToHost, R.down);
+        }
+    }
+    e = cudaStreamSynchronize(R.up); // also covers a matrix that reads less than all of x
     if (e == cudaSuccess)
-        cudaEventElapsedTime(ms, e0, e1);
-    for (int c = 0; c < CSR_OUT_CHUNKS; c++)
-        cudaEventDestroy(done[c]);
-    cudaStreamDestroy(copy_stream);
+        e = cudaStreamSynchronize(0);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(R.down);
     if (rc != SMVP_OK)
         return rc;
     if (e != cudaSuccess)
-        return cuda_fail(e, "overlapped copy-out", __FILE__, __LINE__);
+        return cuda_fail(e, "pipelined pass", __FILE__, __LINE__);
+    float total = 0.f;
+    for (int c = 0; c < PIPE_RANGES; c++)
+    {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, R.t0[c], R.t1[c]);
+        total += t;
+    }
+    *ms = total;
     SMVP_CUDA(cudaGetLastError());
     return SMVP_OK;
 }
@@ -924,18 +1117,29 @@ extern "C" int smvp_csr_mult(smvp_csr *A, const double *x_host, double *y_host, 
         SMVP_CUDA(dev_alloc(&A->d_x, A->cols));
     if (!A->d_y)
         SMVP_CUDA(dev_alloc(&A->d_y, A->rows));
-    if (A->cols > 0)
+    const bool merge = csr_resolve_variant(A, variant) == SMVP_CSR_MERGE && A->rows > 0;
+    // big vectors: pipeline their PCIe transfers with the first / last pass (SMVP_NO_OVERLAP=1: plain copies)
+    const bool pipelined = merge && ((int64_t)A->rows + A->cols) >= (1 << 21) && getenv("SMVP_NO_OVERLAP") == nullptr;
+    int rc = SMVP_OK;
+    // plans outside the timed bracket (the reference builds its format before the loop too)
+    if (A->rows > 0)
+        rc = csr_relabel_plan(A, 0);
+    if (rc == SMVP_OK && pipelined)
+        rc = pipe_plan(A);
+    else if (rc == SMVP_OK && merge)
+        rc = merge_plan(A, pick_merge_cfg(A), 0);
+    if (rc != SMVP_OK)
+        return rc;
+    const bool relabeled = A->relabel_state == 1;
+    const bool upload_under_pass = pipelined && !relabeled; // a relabelled x has to be complete before it is permuted
+    if (A->cols > 0 && !upload_under_pass)
         SMVP_CUDA(cudaMemcpy(A->d_x, x_host, sizeof(double) * (size_t)A->cols, cudaMemcpyHostToDevice));
+    if (relabeled) // once, before the loop, as the reference permutes x for TJDS (main-cli.c:907-923)
+        SMVP_TRY(csr_relabel_x(A, A->d_x, 0));
+    const double *xm = relabeled ? A->x_rel : A->d_x;
     cudaEvent_t e0, e1;
     SMVP_CUDA(cudaEventCreate(&e0));
     SMVP_CUDA(cudaEventCreate(&e1));
-    int rc = SMVP_OK;
-    const bool merge = csr_resolve_variant(A, variant) == SMVP_CSR_MERGE && A->rows > 0;
-    // plan outside the timed bracket (the reference builds its format before the loop too)
-    if (merge)
-        rc = merge_plan(A, pick_merge_cfg(A), 0);
-    // big result vector: overlap its copy-out with the last pass
-    const bool overlap_out = merge && A->rows >= (1 << 20) && getenv("SMVP_NO_OVERLAP_OUT") == nullptr;
     bool y_copied = false;
     for (int it = 0; it < iters && rc == SMVP_OK; it++)
     {
@@ -943,15 +1147,16 @@ extern "C" int smvp_csr_mult(smvp_csr *A, const double *x_host, double *y_host, 
         // fill only keeps the reference's structure observable
         cudaMemsetAsync(A->d_y, 0, sizeof(double) * (size_t)A->rows, 0);
         float ms = 0.f;
-        if (overlap_out && it == iters - 1)
+        const bool first = it == 0, last = it == iters - 1;
+        if (pipelined && ((first && upload_under_pass) || last))
         {
-            rc = csr_mult_last_overlapped(A, y_host, e0, e1, &ms);
-            y_copied = rc == SMVP_OK;
+            rc = csr_mult_pipelined(A, (first && upload_under_pass) ? x_host : nullptr, last ? y_host : nullptr, &ms);
+            y_copied = last && rc == SMVP_OK;
         }
         else
         {
             cudaEventRecord(e0, 0);
-            rc = smvp_csr_mult_device(A, A->d_x, A->d_y, variant, nullptr);
+            rc = csr_mult_launch(A, xm, A->d_y, nullptr, variant, 0);
             cudaEventRecord(e1, 0);
             if (rc != SMVP_OK)
                 break;
@@ -990,5 +1195,6 @@ extern "C" int smvp_csr_info(const smvp_csr *A, smvp_csr_info_t *out)
     out->launches_per_mult[SMVP_CSR_VECTOR] = 1;
     out->launches_per_mult[SMVP_CSR_MERGE] = 2;
     out->launches_per_mult[SMVP_CSR_AUTO] = out->launches_per_mult[out->auto_variant];
+    out->x_relabel = A->relabel_state;
     return SMVP_OK;
 }

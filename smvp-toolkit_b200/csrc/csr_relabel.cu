@@ -1,0 +1,188 @@
+// csr_relabel.cu -- popularity relabelling of the CSR column space (a multiply-side plan; the CSR arrays the
+// reference defines, main-cli.c:61-66, stay untouched and bit-exact).
+//
+// Why: the CSR loop (main-cli.c:410-416) gathers x[col_ind[j]].  On a power-law matrix whose x does not fit
+// the 126 MB L2 (R-MAT scale 26: 537 MB) half of those 8-byte gathers miss L2 and each miss moves a 32-byte
+// DRAM sector: ncu counted 30.6 GB of DRAM traffic for 14.1 GB of algorithmic bytes
+// (profiles/r01_csr_merge_warp_rmat26.txt).  The gathers are far from uniform, though: a few million columns
+// receive most of them -- but they are scattered over the whole index range, so they share their sectors and
+// cache lines with cold columns.
+//
+// What: number the columns by descending entry count (ties keep column order) -- exactly the permutation
+// the TJDS format defines (main-cli.c:868, txtable_comparator_len :209-223) -- and keep
+//     col_rel[j] = rank[col_ind[j]]        one extra int32 per nonzero, read INSTEAD of col_ind by the kernels
+//     x_order[p] = column with rank p      x_rel[p] = x[x_order[p]] is formed once per x
+// The hot columns become one dense prefix of x_rel that stays resident in L2 (and partly in L1).  Entries keep
+// their order inside each row, so every row is summed in exactly the order it was before: y is bit-identical
+// with and without the plan.
+//
+// When (AUTO): x larger than RELABEL_MIN_COLS entries, and the RELABEL_HOT_COLS most popular columns hold at
+// least half of the nonzeros and at least four times their fair share.  Banded and uniform matrices fail the
+// test and keep their natural (already local, or hopeless) order.  SMVP_CSR_RELABEL=1 / 0 forces it on / off.
+#include "common.cuh"
+
+namespace smvp
+{
+
+constexpr int64_t RELABEL_MIN_COLS = 8 << 20; // x of 64 MB and more: beyond what L2 keeps next to the matrix streams
+constexpr int64_t RELABEL_HOT_COLS = 4 << 20; // 32 MB of x: the part expected to stay L2-resident
+
+__global__ void __launch_bounds__(256) relabel_key_kernel(const uint32_t *__restrict__ count, int32_t cols, uint32_t maxc,
+                                                          uint32_t *__restrict__ key, uint32_t *__restrict__ idx)
+{
+    const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < cols)
+    {
+        key[c] = maxc - count[c]; // ascending key == descending count; the stable sort keeps col ascending on ties
+        idx[c] = (uint32_t)c;
+    }
+}
+
+// nonzeros held by the first k columns of the sorted order
+__global__ void __launch_bounds__(256) relabel_cover_kernel(const uint32_t *__restrict__ sorted_key, int32_t k, uint32_t maxc,
+                                                            unsigned long long *__restrict__ sum)
+{
+    unsigned long long t = 0;
+    for (int32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < k; p += gridDim.x * blockDim.x)
+        t += maxc - sorted_key[p];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0 && t)
+        atomicAdd(sum, t);
+}
+
+__global__ void __launch_bounds__(256) relabel_rank_kernel(const uint32_t *__restrict__ sorted_col, int32_t cols,
+                                                           int32_t *__restrict__ x_order, int32_t *__restrict__ rank)
+{
+    const int32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < cols)
+    {
+        const int32_t c = (int32_t)sorted_col[p];
+        x_order[p] = c;
+        rank[c] = p;
+    }
+}
+
+__global__ void __launch_bounds__(256) relabel_cols_kernel(const int32_t *__restrict__ col_ind, int64_t nnz,
+                                                           const int32_t *__restrict__ rank, int32_t *__restrict__ col_rel)
+{
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += (int64_t)gridDim.x * blockDim.x)
+        col_rel[j] = __ldg(rank + __ldg(col_ind + j));
+}
+
+__global__ void __launch_bounds__(256) relabel_permute_x_kernel(const double *__restrict__ x, const int32_t *__restrict__ x_order,
+                                                                int32_t cols, double *__restrict__ x_rel)
+{
+    for (int32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < cols; p += gridDim.x * blockDim.x)
+        x_rel[p] = __ldg(x + __ldg(x_order + p));
+}
+
+// decides (once per handle) and, if the plan is worth it, builds col_rel / x_order / x_rel.  Synchronous.
+int csr_relabel_plan(smvp_csr *A, cudaStream_t s)
+{
+    if (A->relabel_state != 0)
+        return SMVP_OK;
+    const char *env = getenv("SMVP_CSR_RELABEL");
+    const int forced = (env && env[0] == '1') ? 1 : (env && env[0] == '0') ? -1 : 0;
+    const int32_t cols = A->cols;
+    if (forced < 0 || A->nnz == 0 || cols == 0 || (forced == 0 && cols < RELABEL_MIN_COLS))
+    {
+        A->relabel_state = -1;
+        return SMVP_OK;
+    }
+    uint32_t *count = nullptr, *d_max = nullptr, *key_a = nullptr, *key_b = nullptr, *idx_a = nullptr, *idx_b = nullptr;
+    unsigned long long *d_cover = nullptr;
+    int32_t *rank = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(count);
+        cudaFree(d_max);
+        cudaFree(key_a);
+        cudaFree(key_b);
+        cudaFree(idx_a);
+        cudaFree(idx_b);
+        cudaFree(d_cover);
+        cudaFree(rank);
+    };
+    auto body = [&]() -> int {
+        const unsigned cblocks = (unsigned)ceil_div64(cols, 256);
+        SMVP_CUDA(dev_alloc(&count, (int64_t)cols + 1));
+        SMVP_CUDA(dev_alloc(&d_max, 1));
+        SMVP_CUDA(dev_alloc(&d_cover, 1));
+        SMVP_CUDA(dev_alloc(&key_a, cols));
+        SMVP_CUDA(dev_alloc(&key_b, cols));
+        SMVP_CUDA(dev_alloc(&idx_a, cols));
+        SMVP_CUDA(dev_alloc(&idx_b, cols));
+        SMVP_TRY(histogram_i32(A->col_ind, A->nnz, count, (int64_t)cols + 1, s));
+        SMVP_TRY(max_u32(count, cols, d_max, s));
+        uint32_t maxc = 0;
+        SMVP_CUDA(cudaMemcpyAsync(&maxc, d_max, sizeof(maxc), cudaMemcpyDeviceToHost, s));
+        SMVP_CUDA(cudaStreamSynchronize(s));
+        SMVP_LAUNCH(relabel_key_kernel, cblocks, 256, 0, s, (const uint32_t *)count, cols, maxc, key_a, idx_a);
+        uint32_t *rk = nullptr, *ri = nullptr;
+        const int lo = 0, hi = bits_for(maxc + 1u);
+        SMVP_TRY(radix_sort_pairs<uint32_t>(key_a, idx_a, key_b, idx_b, cols, &lo, &hi, 1, &rk, &ri, s));
+        if (forced == 0)
+        {
+            const int32_t k = (int32_t)(cols < RELABEL_HOT_COLS ? cols : RELABEL_HOT_COLS);
+            SMVP_CUDA(cudaMemsetAsync(d_cover, 0, sizeof(unsigned long long), s));
+            SMVP_LAUNCH(relabel_cover_kernel, (unsigned)device_props().sms * 8, 256, 0, s, (const uint32_t *)rk, k, maxc, d_cover);
+            unsigned long long cover = 0;
+            SMVP_CUDA(cudaMemcpyAsync(&cover, d_cover, sizeof(cover), cudaMemcpyDeviceToHost, s));
+            SMVP_CUDA(cudaStreamSynchronize(s));
+            const double share = (double)cover / (double)A->nnz, fair = (double)k / (double)cols;
+            if (!(share >= 0.5 && share >= 4.0 * fair))
+            {
+                A->relabel_state = -1;
+                return SMVP_OK;
+            }
+        }
+        SMVP_CUDA(dev_alloc(&rank, cols));
+        SMVP_CUDA(dev_alloc(&A->x_order, cols));
+        SMVP_CUDA(dev_alloc(&A->x_rel, cols));
+        SMVP_CUDA(dev_alloc(&A->col_rel, A->nnz));
+        SMVP_LAUNCH(relabel_rank_kernel, cblocks, 256, 0, s, (const uint32_t *)ri, cols, A->x_order, rank);
+        int64_t blocks = ceil_div64(A->nnz, 256 * 4);
+        const int64_t cap = (int64_t)device_props().sms * 16;
+        SMVP_LAUNCH(relabel_cols_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, s, (const int32_t *)A->col_ind, A->nnz,
+                    (const int32_t *)rank, A->col_rel);
+        SMVP_CUDA(cudaStreamSynchronize(s));
+        SMVP_CUDA(cudaGetLastError());
+        A->device_bytes += 4 * A->nnz + 12 * (int64_t)cols;
+        A->relabel_state = 1;
+        return SMVP_OK;
+    };
+    const int rc = body();
+    cleanup();
+    if (rc != SMVP_OK)
+    {
+        cudaFree(A->x_order);
+        cudaFree(A->x_rel);
+        cudaFree(A->col_rel);
+        A->x_order = A->col_rel = nullptr;
+        A->x_rel = nullptr;
+    }
+    return rc;
+}
+
+// x_rel = x in rank order (asynchronous on s)
+int csr_relabel_x(smvp_csr *A, const double *d_x, cudaStream_t s)
+{
+    int64_t blocks = ceil_div64(A->cols, 256 * 4);
+    const int64_t cap = (int64_t)device_props().sms * 8;
+    SMVP_LAUNCH(relabel_permute_x_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, s, d_x, (const int32_t *)A->x_order, A->cols,
+                A->x_rel);
+    SMVP_CUDA(cudaGetLastError());
+    return SMVP_OK;
+}
+
+void csr_relabel_release(smvp_csr *A)
+{
+    cudaFree(A->x_order);
+    cudaFree(A->x_rel);
+    cudaFree(A->col_rel);
+    A->x_order = A->col_rel = nullptr;
+    A->x_rel = nullptr;
+}
+
+} // namespace smvp

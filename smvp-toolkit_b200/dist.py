@@ -314,7 +314,12 @@ class RowBlockCsr:
         self._source_desc = source.desc
 
     def set_x(self, x, stream=None):
-        self.x = x
+        """The x of the following steps (constant over the reference's -n loop): smvp_csr_set_x_device on every
+        block, so a handle that relabels its column space permutes x once here and not once per pass."""
+        self._x_keep = x
+        for A in self.subs:
+            A.set_x_device(x, stream)
+        self.x = None  # passes use the x declared above
 
     def multiply(self, stream=None):
         import torch
@@ -414,7 +419,7 @@ class RowBlockCsr:
             if s1 > s0:
                 self._xpad[s0:s1].copy_(hx[s0:s1], non_blocking=True)
             dist.all_gather_into_tensor(self._xpad, self._xpad[s0:s0 + per])
-            self.x = self._xpad[:self.N]
+            self.set_x(self._xpad[:self.N], stream)
             self.step(stream)
             hy.copy_(self.y_local, non_blocking=True)
             stream.synchronize()

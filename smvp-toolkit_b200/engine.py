@@ -44,7 +44,7 @@ class _CsrInfo(ctypes.Structure):
     _fields_ = [("rows", ctypes.c_int32), ("cols", ctypes.c_int32), ("nnz", ctypes.c_int64),
                 ("max_row_nnz", ctypes.c_int32), ("auto_variant", ctypes.c_int32), ("input_order", ctypes.c_int32),
                 ("bytes_per_mult", ctypes.c_int64), ("device_bytes", ctypes.c_int64),
-                ("launches_per_mult", ctypes.c_int32 * 3)]
+                ("launches_per_mult", ctypes.c_int32 * 3), ("x_relabel", ctypes.c_int32)]
 
 
 class _TjdsInfo(ctypes.Structure):
@@ -71,6 +71,7 @@ SIGNATURES = {
     "smvp_tjds_mult": (_int, [_vp, _vp, _vp, _int, _vp, _int, _i32]),
     "smvp_csr_build_device": (_int, [_vp, _vp, _vp, _i32, _i32, _i64, _pp]),
     "smvp_tjds_build_device": (_int, [_vp, _vp, _vp, _i32, _i32, _i64, _pp]),
+    "smvp_csr_set_x_device": (_int, [_vp, _vp, _vp]),
     "smvp_csr_mult_device": (_int, [_vp, _vp, _vp, _int, _vp]),
     "smvp_csr_mult_device_fanout": (_int, [_vp, _vp, _vp, _int, _int, _vp]),
     "smvp_tjds_set_x_device": (_int, [_vp, _vp, _vp]),
@@ -235,8 +236,20 @@ class CsrMatrix:
         _check(lib().smvp_csr_mult(self._h, _ptr(x), _ptr(y), iters, _ptr(ms), variant), "smvp_csr_mult")
         return y, TimeData(ms)
 
+    def set_x_device(self, d_x, stream=None):
+        """Declare the x of the following passes (smvp_csr_set_x_device); pass d_x=None to mult_device afterwards."""
+        _check(lib().smvp_csr_set_x_device(self._h, _ptr(d_x), _stream(stream)), "smvp_csr_set_x_device")
+
     def mult_device(self, d_x, d_y, variant=CSR_AUTO, stream=None):
+        """One pass y = A x; d_x=None uses the x last given to set_x_device."""
         _check(lib().smvp_csr_mult_device(self._h, _ptr(d_x), _ptr(d_y), variant, _stream(stream)), "smvp_csr_mult_device")
+
+    @property
+    def x_relabel(self):
+        """1: the multiply reads popularity-relabelled columns, -1: natural order, 0: not decided yet."""
+        info = _CsrInfo()
+        _check(lib().smvp_csr_info(self._h, ctypes.byref(info)), "smvp_csr_info")
+        return info.x_relabel
 
     def mult_device_fanout(self, d_x, y_ptrs, variant=CSR_AUTO, stream=None):
         """y = A x stored into every destination of y_ptrs (device addresses, possibly peer-mapped)."""

@@ -287,25 +287,136 @@ def test_device_path_medium(eng, kind):
     T.free()
 
 
-def test_host_call_overlapped_copy_out(eng, monkeypatch):
-    """smvp_csr_mult on a matrix with > 2^20 rows copies y out range by range while later tile ranges still multiply;
-    the result must equal the plain path bit for bit and the oracle within 1e-12."""
+@pytest.mark.parametrize("banded", [True, False])
+def test_host_call_pipelined_transfers(eng, monkeypatch, banded):
+    """smvp_csr_mult on a big matrix uploads x piece by piece under the first pass (a tile range starts once the
+    leading part of x it reads has arrived) and copies y out range by range under the last pass.  Results must equal
+    the plain copy-multiply-copy path bit for bit, for 1, 2 and 3 iterations, from pageable and from pinned host
+    buffers, on a banded matrix (ranges really start early) and on one whose rows reach every column."""
+    import ctypes
+
+    import torch
+
     m = n = (1 << 20) + 12345
     r = np.arange(m, dtype=np.int64)
-    rows = np.concatenate([r, r[1:], r[:-1], r[::7]])
-    cols = np.concatenate([r, r[1:] - 1, r[:-1] + 1, (r[::7] * 31 + 5) % n])
+    rows = [r, r[1:], r[:-1], r[3000:], r[:-3000]]
+    cols = [r, r[1:] - 1, r[:-1] + 1, r[3000:] - 3000, r[:-3000] + 3000]
+    if not banded:
+        rows.append(r[::7])
+        cols.append((r[::7] * 31 + 5) % n)
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
     key = np.unique(rows * n + cols)
     rng = np.random.default_rng(8)
     coo = oracle.make_coo(key // n, key % n, rng.uniform(-1, 1, len(key)))
     x = rng.uniform(-1, 1, n)
     y_ref = oracle.csr_mult(*oracle.csr_build(coo, m, n), x)
     A = eng.CsrMatrix.build(coo, m, n)
-    y1, td = A.mult(x, iters=2, variant=eng.CSR_MERGE)
-    assert util.rel_l2(y1, y_ref) <= TOL and len(td.time_each) == 2 and td.time_min > 0
-    monkeypatch.setenv("SMVP_NO_OVERLAP_OUT", "1")
-    y2, _ = A.mult(x, iters=1, variant=eng.CSR_MERGE)
-    assert np.array_equal(y1.view(np.int64), y2.view(np.int64))
+    outs = []
+    for iters in (1, 2, 3):
+        y, td = A.mult(x, iters=iters, variant=eng.CSR_MERGE)
+        assert util.rel_l2(y, y_ref) <= TOL and len(td.time_each) == iters and td.time_min > 0
+        outs.append(y)
+    # pinned buffers straight through the C ABI, with a different x so that stale device data would show
+    x2 = rng.uniform(-1, 1, n)
+    hx = torch.as_tensor(x2).pin_memory()
+    hy = torch.full((m,), float("nan"), dtype=torch.float64).pin_memory()
+    rc = eng.lib().smvp_csr_mult(A._h, ctypes.c_void_p(hx.data_ptr()), ctypes.c_void_p(hy.data_ptr()), 1, None, eng.CSR_MERGE)
+    assert rc == 0
+    y_pinned = hy.numpy().copy()
+    monkeypatch.setenv("SMVP_NO_OVERLAP", "1")
+    y_plain, _ = A.mult(x, iters=1, variant=eng.CSR_MERGE)
+    y2_plain, _ = A.mult(x2, iters=1, variant=eng.CSR_MERGE)
+    for y in outs:
+        assert np.array_equal(y.view(np.int64), y_plain.view(np.int64))
+    assert np.array_equal(y_pinned.view(np.int64), y2_plain.view(np.int64))
     A.free()
+
+
+def _powerlaw_coo(rng, m, n, nnz, power):
+    """Unique (row, col) pairs whose columns follow a power law spread over the whole index range (the hot columns
+    are scattered by a multiplicative hash, as in an R-MAT matrix, not contiguous)."""
+    rows = rng.integers(0, m, nnz)
+    hot = np.minimum((n * rng.random(nnz) ** power).astype(np.int64), n - 1)
+    cols = (hot * 2654435761) % n if math.gcd(2654435761, n) == 1 else hot
+    key = np.unique(rows * n + cols)
+    return oracle.make_coo(key // n, key % n, rng.uniform(-1, 1, len(key)))
+
+
+def test_csr_relabel_forced_bit_identical(eng, monkeypatch):
+    """The popularity relabelling of the column space (csr_relabel.cu) is a multiply-side plan: the exported CSR
+    arrays stay bit-exact against the oracle, and because entries keep their order inside each row, y is
+    bit-identical with and without it -- for both kernels, through every entry point."""
+    import torch
+
+    rng = np.random.default_rng(77)
+    m, n = 30011, 40009
+    coo = _powerlaw_coo(rng, m, n, 600000, 4.0)
+    x = rng.uniform(-1, 1, n)
+    rp, ci, va = oracle.csr_build(coo, m, n)
+    y_ref = oracle.csr_mult(rp, ci, va, x)
+    monkeypatch.setenv("SMVP_CSR_RELABEL", "0")
+    P = eng.CsrMatrix.build(coo, m, n)
+    plain = {v: P.mult(x, iters=1, variant=v)[0] for v in (eng.CSR_VECTOR, eng.CSR_MERGE)}
+    assert P.x_relabel == -1
+    monkeypatch.setenv("SMVP_CSR_RELABEL", "1")
+    A = eng.CsrMatrix.build(coo, m, n)
+    for v in (eng.CSR_VECTOR, eng.CSR_MERGE):
+        y, td = A.mult(x, iters=3, variant=v)
+        assert A.x_relabel == 1
+        assert util.rel_l2(y, y_ref) <= TOL
+        assert np.array_equal(y.view(np.int64), plain[v].view(np.int64)), "relabelled y differs from the plain y"
+    g = A.export()
+    assert np.array_equal(g[0], rp) and np.array_equal(g[1], ci) and np.array_equal(g[2].view(np.int64), va.view(np.int64))
+    # device entry points: explicit x, declared x (d_x = NULL), fan-out
+    d_x = torch.as_tensor(x, device="cuda")
+    d_y = torch.full((m,), float("nan"), dtype=torch.float64, device="cuda")
+    for v in (eng.CSR_VECTOR, eng.CSR_MERGE):
+        A.mult_device(d_x, d_y, v)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_y.cpu().numpy().view(np.int64), plain[v].view(np.int64))
+    x2 = rng.uniform(-1, 1, n)
+    d_x2 = torch.as_tensor(x2, device="cuda")
+    A.set_x_device(d_x2)
+    P.set_x_device(d_x2)
+    outs = [torch.full((m,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(2)]
+    A.mult_device(None, outs[0], eng.CSR_MERGE)
+    P.mult_device(None, outs[1], eng.CSR_MERGE)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    assert util.rel_l2(outs[0].cpu().numpy(), oracle.csr_mult(rp, ci, va, x2)) <= TOL
+    fan = [torch.full((m,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(2)]
+    A.mult_device_fanout(None, [f.data_ptr() for f in fan], eng.CSR_MERGE)
+    torch.cuda.synchronize()
+    assert torch.equal(fan[0], outs[0]) and torch.equal(fan[1], outs[0])
+    # a handle that never saw set_x_device refuses d_x = NULL
+    B = eng.CsrMatrix.build(coo, m, n)
+    with pytest.raises(eng.SmvpError):
+        B.mult_device(None, d_y, eng.CSR_MERGE)
+    for h in (A, B, P):
+        h.free()
+
+
+def test_csr_relabel_auto_decision(eng):
+    """AUTO relabels only when x is large AND the 4 Mi most popular columns hold most of the nonzeros (>= 1/2 and
+    >= 4x their fair share, which needs more than 16 Mi columns):
+    a power-law matrix qualifies, a uniform one of the same shape does not; results stay within 1e-12 either way.
+    The big-matrix host path (pipelined copy-out, whole-x upload + permutation) is exercised on the way."""
+    rng = np.random.default_rng(78)
+    m, n, nnz = 1 << 20, (17 << 20) + 5, 6000000
+    x = rng.uniform(-1, 1, n)
+    for power, expect in ((8.0, 1), (1.0, -1)):
+        coo = _powerlaw_coo(rng, m, n, nnz, power)
+        rp, ci, va = oracle.csr_build(coo, m, n)
+        y_ref = oracle.csr_mult(rp, ci, va, x)
+        A = eng.CsrMatrix.build(coo, m, n)
+        assert A.x_relabel == 0  # decided lazily, at the first pass
+        for iters in (1, 2):
+            y, _ = A.mult(x, iters=iters, variant=eng.CSR_MERGE)
+            assert util.rel_l2(y, y_ref) <= TOL
+        assert A.x_relabel == expect, (power, A.x_relabel)
+        g = A.export()
+        assert np.array_equal(g[1], ci)
+        A.free()
 
 
 def test_fanout_and_write_only_y(eng):
