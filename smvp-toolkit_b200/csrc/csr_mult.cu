@@ -903,9 +903,9 @@ extern "C" int smvp_csr_mult_device_fanout(smvp_csr *A, const double *d_x, doubl
 }
 
 // ------------------------------------------------------------------ host-vector entry point
-// For large matrices the pass that touches the host is cut into PIPE_RANGES consecutive ranges of merge-path
+// For large matrices the pass that touches the host is cut into consecutive ranges (32 by default) of merge-path
 // tiles and pipelined against both PCIe directions:
-//   * first pass: x goes up in PIPE_XCHUNKS pieces on an upload stream; range c starts as soon as the leading
+//   * first pass: x goes up in pieces (64 by default) on an upload stream; range c starts as soon as the leading
 //     part of x it reads (x[0 .. xneed_c), xneed_c = 1 + the largest column index among its nonzeros, a property
 //     of the matrix found once per handle) has arrived.  A banded matrix (stencils, meshes) therefore multiplies
 //     while x is still uploading; a matrix whose first rows reach the last column simply waits for all of x.
@@ -914,8 +914,20 @@ extern "C" int smvp_csr_mult_device_fanout(smvp_csr *A, const double *d_x, doubl
 // With iters == 1 both happen in the same pass and the call costs about ONE vector transfer (PCIe is full
 // duplex) instead of upload + multiply + download back to back.  ms_each still reports the multiply alone: the
 // sum of the ranges' own event brackets, each opened after the range's wait for x.
-constexpr int PIPE_RANGES = 32;
-constexpr int PIPE_XCHUNKS = 64;
+constexpr int PIPE_MAX_RANGES = 64;   // == capacity of smvp_csr::pipe_tile / pipe_row / pipe_xneed (common.cuh)
+constexpr int PIPE_MAX_XCHUNKS = 128;
+
+static int env_int(const char *name, int dflt, int lo, int hi)
+{
+    const char *e = getenv(name);
+    if (!e || !e[0])
+        return dflt;
+    const int v = atoi(e);
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+// defaults from the sweep on B200 (tools/sweep_e2e.py, profiles/): tuning hooks SMVP_PIPE_RANGES / SMVP_PIPE_XCHUNKS
+static int pipe_ranges() { return env_int("SMVP_PIPE_RANGES", 32, 1, PIPE_MAX_RANGES); }
+static int pipe_xchunks() { return env_int("SMVP_PIPE_XCHUNKS", 64, 1, PIPE_MAX_XCHUNKS); }
 
 __global__ void __launch_bounds__(256) col_max_kernel(const int32_t *__restrict__ col_ind, int64_t n0, int64_t n1,
                                                       int32_t *__restrict__ out)
@@ -933,26 +945,27 @@ __global__ void __launch_bounds__(256) col_max_kernel(const int32_t *__restrict_
 static int pipe_plan(smvp_csr *A)
 {
     SMVP_TRY(merge_plan(A, pick_merge_cfg(A), 0));
-    if (A->pipe_cfg == A->merge_cfg)
+    const int NR = pipe_ranges();
+    if (A->pipe_cfg == A->merge_cfg && A->pipe_ranges == NR)
         return SMVP_OK;
     const int32_t T = A->merge_tiles;
     const int64_t tile_items = A->merge_cfg;
     int32_t *d_max = nullptr;
-    SMVP_CUDA(dev_alloc(&d_max, PIPE_RANGES));
-    cudaError_t e = cudaMemset(d_max, 0xff, sizeof(int32_t) * PIPE_RANGES); // -1: the range reads no x at all
-    for (int c = 0; c <= PIPE_RANGES && e == cudaSuccess; c++)
+    SMVP_CUDA(dev_alloc(&d_max, PIPE_MAX_RANGES));
+    cudaError_t e = cudaMemset(d_max, 0xff, sizeof(int32_t) * PIPE_MAX_RANGES); // -1: the range reads no x at all
+    for (int c = 0; c <= NR && e == cudaSuccess; c++)
     {
-        A->pipe_tile[c] = (int32_t)((int64_t)T * c / PIPE_RANGES);
+        A->pipe_tile[c] = (int32_t)((int64_t)T * c / NR);
         // rows consumed before each boundary tile (tile_row[T] = rows)
         e = cudaMemcpy(&A->pipe_row[c], A->tile_row + A->pipe_tile[c], sizeof(int32_t), cudaMemcpyDeviceToHost);
     }
-    for (int c = 0; c < PIPE_RANGES && e == cudaSuccess; c++)
+    for (int c = 0; c < NR && e == cudaSuccess; c++)
     {
         // nonzeros of the range: merge items before the boundary minus the row ends among them
         int64_t n0 = (int64_t)A->pipe_tile[c] * tile_items - A->pipe_row[c];
         int64_t n1 = (int64_t)A->pipe_tile[c + 1] * tile_items - A->pipe_row[c + 1];
         n0 = n0 < A->nnz ? n0 : A->nnz;
-        n1 = (c + 1 == PIPE_RANGES || n1 > A->nnz) ? A->nnz : n1;
+        n1 = (c + 1 == NR || n1 > A->nnz) ? A->nnz : n1;
         if (n1 > n0)
         {
             int64_t grid = ceil_div64(n1 - n0, 256 * 16);
@@ -961,34 +974,35 @@ static int pipe_plan(smvp_csr *A)
                         d_max + c);
         }
     }
-    int32_t h_max[PIPE_RANGES];
+    int32_t h_max[PIPE_MAX_RANGES];
     if (e == cudaSuccess)
         e = cudaMemcpy(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost);
     cudaFree(d_max);
     if (e != cudaSuccess)
         return cuda_fail(e, "pipe_plan", __FILE__, __LINE__);
     int32_t need = 0; // x arrives front to back, so a range needs everything up to the largest column seen so far
-    for (int c = 0; c < PIPE_RANGES; c++)
+    for (int c = 0; c < NR; c++)
     {
         need = h_max[c] + 1 > need ? h_max[c] + 1 : need;
         A->pipe_xneed[c] = need;
     }
     A->pipe_cfg = A->merge_cfg;
+    A->pipe_ranges = NR;
     return SMVP_OK;
 }
 
 struct PipeResources
 {
     cudaStream_t up = nullptr, down = nullptr;
-    cudaEvent_t x_ready[PIPE_XCHUNKS] = {}, done[PIPE_RANGES] = {}, t0[PIPE_RANGES] = {}, t1[PIPE_RANGES] = {};
+    cudaEvent_t x_ready[PIPE_MAX_XCHUNKS] = {}, done[PIPE_MAX_RANGES] = {}, t0[PIPE_MAX_RANGES] = {}, t1[PIPE_MAX_RANGES] = {};
     cudaError_t create()
     {
         cudaError_t e = cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking);
         if (e == cudaSuccess)
             e = cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking);
-        for (int c = 0; c < PIPE_XCHUNKS && e == cudaSuccess; c++)
+        for (int c = 0; c < PIPE_MAX_XCHUNKS && e == cudaSuccess; c++)
             e = cudaEventCreateWithFlags(&x_ready[c], cudaEventDisableTiming);
-        for (int c = 0; c < PIPE_RANGES && e == cudaSuccess; c++)
+        for (int c = 0; c < PIPE_MAX_RANGES && e == cudaSuccess; c++)
         {
             e = cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming);
             if (e == cudaSuccess)
@@ -1000,10 +1014,10 @@ struct PipeResources
     }
     ~PipeResources()
     {
-        for (int c = 0; c < PIPE_XCHUNKS; c++)
+        for (int c = 0; c < PIPE_MAX_XCHUNKS; c++)
             if (x_ready[c])
                 cudaEventDestroy(x_ready[c]);
-        for (int c = 0; c < PIPE_RANGES; c++)
+        for (int c = 0; c < PIPE_MAX_RANGES; c++)
         {
             if (done[c])
                 cudaEventDestroy(done[c]);
@@ -1047,10 +1061,11 @@ static int csr_mult_pipelined(smvp_csr *A, const double *x_host, double *y_host,
         A->pipe_res = fresh;
     }
     PipeResources &R = *static_cast<PipeResources *>(A->pipe_res);
-    const int64_t xchunk = ((ceil_div64(A->cols, PIPE_XCHUNKS) + 63) / 64) * 64; // entries per upload piece (512 B multiple)
+    const int NR = A->pipe_ranges, NX = pipe_xchunks();
+    const int64_t xchunk = ((ceil_div64(A->cols, NX) + 63) / 64) * 64; // entries per upload piece (512 B multiple)
     if (x_host)
     {
-        for (int k = 0; k < PIPE_XCHUNKS; k++)
+        for (int k = 0; k < NX; k++)
         {
             const int64_t a = (int64_t)k * xchunk, b = a + xchunk < A->cols ? a + xchunk : A->cols;
             if (b > a)
@@ -1061,12 +1076,12 @@ static int csr_mult_pipelined(smvp_csr *A, const double *x_host, double *y_host,
     int rc = SMVP_OK;
     const double *xm = A->relabel_state == 1 ? A->x_rel : A->d_x; // callers upload under the pass only without relabelling
     int waited = -1; // last upload piece the compute stream already waits for
-    for (int c = 0; c < PIPE_RANGES && rc == SMVP_OK; c++)
+    for (int c = 0; c < NR && rc == SMVP_OK; c++)
     {
         if (x_host && A->pipe_xneed[c] > 0)
         {
             int k = (int)(((int64_t)A->pipe_xneed[c] - 1) / xchunk);
-            k = k < PIPE_XCHUNKS ? k : PIPE_XCHUNKS - 1;
+            k = k < NX ? k : NX - 1;
             if (k > waited)
             {
                 cudaStreamWaitEvent(0, R.x_ready[k], 0); // pieces are in stream order: k implies all before it
@@ -1096,7 +1111,7 @@ static int csr_mult_pipelined(smvp_csr *A, const double *x_host, double *y_host,
     if (e != cudaSuccess)
         return cuda_fail(e, "pipelined pass", __FILE__, __LINE__);
     float total = 0.f;
-    for (int c = 0; c < PIPE_RANGES; c++)
+    for (int c = 0; c < NR; c++)
     {
         float t = 0.f;
         cudaEventElapsedTime(&t, R.t0[c], R.t1[c]);
