@@ -83,6 +83,26 @@ __device__ __forceinline__ double ldg_x(const double *p, uint64_t pol)
     return __ldg(p);
 #endif
 }
+// x gather of a popularity-relabelled matrix (csr_relabel.cu): the column index IS the popularity rank, so the
+// load can say how long the line deserves to live.  rank < hot_l1: keep in L1; rank < hot_l2: keep in L2
+// (evict-last) while the matrix streams and the cold gathers pass through evict-first and do not allocate in L1.
+__device__ __forceinline__ double ldg_x_ranked(const double *x, int32_t c, int32_t hot_l1, int32_t hot_l2, uint64_t pol_last,
+                                               uint64_t pol_first)
+{
+    double v;
+    const uint64_t pol = c < hot_l2 ? pol_last : pol_first;
+    if (c < hot_l1)
+        asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(x + c), "l"(pol));
+    else
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(x + c), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ double ldg_x_pinned(const double *p) // plain read-only load whose position in the code is kept
+{
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ uint64_t l2_evict_first_policy()
 {
     uint64_t pol;
@@ -114,6 +134,9 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
 #endif
 #ifndef SMVP_SCAN_EXIT
 #define SMVP_SCAN_EXIT 0
+#endif
+#ifndef SMVP_PHASED_PLAIN
+#define SMVP_PHASED_PLAIN 0 // natural-order matrices: issue indices / gathers / products in three pinned phases too
 #endif
 #ifndef SMVP_X_EVICT_LAST
 #define SMVP_X_EVICT_LAST 0 // gather x with an L2 evict-last policy: measured 1 % on the stencil, 0 % on R-MAT -> off
@@ -360,12 +383,12 @@ __device__ __forceinline__ TileView make_tile(int32_t r0, int32_t r1, int32_t t,
 // never meets a block-wide barrier: warps of a CTA drift apart freely, so while one waits for HBM
 // or for its x gathers the others walk.  Rows cut by lane boundaries are stitched with a segmented
 // warp scan (__shfl_up_sync), rows cut by tile boundaries by the fix-up kernel -- fixed order, no atomics.
-template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT>
+template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT, bool RANKED>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     csr_merge_warp_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_ind, const double *__restrict__ val,
                           const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int32_t rows,
                           int64_t nnz, int32_t tile_begin, int32_t num_tiles, double *__restrict__ head_val,
-                          double *__restrict__ carry_val, const __grid_constant__ YFan fan)
+                          double *__restrict__ carry_val, const __grid_constant__ YFan fan, int32_t hot_l1, int32_t hot_l2)
 {
     // processes tiles [tile_begin, num_tiles): a sub-range lets the host overlap the copy-out of finished rows
     static_assert(STAGES == 1, "one stage per warp: deeper rings lost to more resident warps in every sweep");
@@ -391,6 +414,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 #else
     const uint64_t xpol = 0;
 #endif
+    const uint64_t pol_last = RANKED ? l2_evict_last_policy() : 0, pol_first = RANKED ? l2_evict_first_policy() : 0;
+    auto gather = [&](int32_t c) -> double {
+        return RANKED ? ldg_x_ranked(x, c, hot_l1, hot_l2, pol_last, pol_first) : ldg_x(x + c, xpol);
+    };
     const int32_t warp_stride = (int32_t)gridDim.x * WARPS;
     auto issue = [&](const TileView &v) { // lane 0 only
         mbar_expect_tx(my_bar, v.vb + v.cb + v.rb);
@@ -512,7 +539,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             {
                 const uint32_t j = (uint32_t)min(j0 + q, jmax);
                 const int32_t c = lds_s32(scol + 4u * j);
-                prod[q] = __dmul_rn(lds_f64(sval + 8u * j), ldg_x(x + c, xpol));
+                prod[q] = __dmul_rn(lds_f64(sval + 8u * j), gather(c));
             }
         }
         else
@@ -522,15 +549,38 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                 prod[q] = 0.0;
         }
 #else
-#pragma unroll
-        for (int q = 0; q < IPT; q++)
+        if (RANKED || SMVP_PHASED_PLAIN)
         {
-            prod[q] = 0.0;
-            if (q < cnt)
+            // three phases, pinned by volatile asm: all column indices, then every gather of the lane, then the products
+            // (random columns: the loads are the latency, so all IPT of them must be in flight together)
+            int32_t cq[IPT];
+#pragma unroll
+            for (int q = 0; q < IPT; q++)
+                cq[q] = q < cnt ? lds_s32(scol + 4u * (uint32_t)(j0 + q)) : 0;
+#pragma unroll
+            for (int q = 0; q < IPT; q++)
             {
-                const uint32_t j = (uint32_t)(j0 + q);
-                const int32_t c = lds_s32(scol + 4u * j);
-                prod[q] = __dmul_rn(lds_f64(sval + 8u * j), ldg_x(x + c, xpol));
+                prod[q] = 0.0;
+                if (q < cnt)
+                    prod[q] = RANKED ? ldg_x_ranked(x, cq[q], hot_l1, hot_l2, pol_last, pol_first) : ldg_x_pinned(x + cq[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < IPT; q++)
+                if (q < cnt)
+                    prod[q] = __dmul_rn(lds_f64(sval + 8u * (uint32_t)(j0 + q)), prod[q]);
+        }
+        else
+        {
+#pragma unroll
+            for (int q = 0; q < IPT; q++)
+            {
+                prod[q] = 0.0;
+                if (q < cnt)
+                {
+                    const uint32_t j = (uint32_t)(j0 + q);
+                    const int32_t c = lds_s32(scol + 4u * j);
+                    prod[q] = __dmul_rn(lds_f64(sval + 8u * j), gather(c));
+                }
             }
         }
 #endif
@@ -746,13 +796,24 @@ static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
     X(5, 2, 7, 1, 16)       \
     X(6, 2, 9, 1, 16)
 
-template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT>
+// how much of the rank-ordered x a relabelled multiply asks L1 / L2 to retain (entries; SMVP_HOT_L1 / SMVP_HOT_L2)
+static void hot_limits(int32_t *l1, int32_t *l2)
+{
+    const char *e1 = getenv("SMVP_HOT_L1"), *e2 = getenv("SMVP_HOT_L2");
+    *l1 = e1 && e1[0] ? atoi(e1) : 8192;     // 64 KB
+    *l2 = e2 && e2[0] ? atoi(e2) : (4 << 20); // 32 MB
+}
+
+template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT, bool RANKED>
 static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, const YFan *fanp, cudaStream_t s, int32_t tile_begin,
                          int32_t tile_end)
 {
     using Shape = MergeShape<32, IPT, STAGES>;
     constexpr int SMEM = WARPS * Shape::SMEM_BYTES;
-    auto kern = csr_merge_warp_kernel<WARPS, IPT, STAGES, MINB, FANOUT>;
+    auto kern = csr_merge_warp_kernel<WARPS, IPT, STAGES, MINB, FANOUT, RANKED>;
+    int32_t hot_l1 = 0, hot_l2 = 0;
+    if (RANKED)
+        hot_limits(&hot_l1, &hot_l2);
     const YFan fan = fanp ? *fanp : YFan();
     static thread_local int configured_dev = -1;
     static thread_local int resident = 1;
@@ -774,7 +835,7 @@ static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, cons
     if (grid > 0)
     {
         SMVP_LAUNCH(kern, (unsigned)grid, WARPS * 32, SMEM, s, A->row_ptr, mult_cols(A), A->val, d_x, d_y, A->tile_row, A->rows,
-                    A->nnz, tile_begin, tile_end, A->head_val, A->carry_val, fan);
+                    A->nnz, tile_begin, tile_end, A->head_val, A->carry_val, fan, hot_l1, hot_l2);
         SMVP_LAUNCH(merge_fixup_kernel<FANOUT>, (unsigned)ceil_div64(ntiles, 256), 256, 0, s, (const int32_t *)A->tile_row,
                     (const double *)A->head_val, (const double *)A->carry_val, tile_begin, tile_end, d_y, fan);
     }
@@ -803,12 +864,18 @@ static int csr_mult_merge(smvp_csr *A, const double *d_x, double *d_y, const YFa
     SMVP_TRY(merge_plan(A, cfg, s));
     if (tile_end < 0)
         tile_end = A->merge_tiles;
+    // a relabelled handle indexes x by popularity rank: the gathers carry cache-retention hints (SMVP_RANKED_HINTS=0: off)
+    const char *rh = getenv("SMVP_RANKED_HINTS");
+    const bool ranked = A->relabel_state == 1 && !(rh && rh[0] == '0');
     switch (cfg)
     {
-#define X(id, wp, i, st, mb)                                                                              \
-    case id:                                                                                              \
-        return fan ? launch_wmerge<wp, i, st, mb, true>(A, d_x, d_y, fan, s, tile_begin, tile_end)        \
-                   : launch_wmerge<wp, i, st, mb, false>(A, d_x, d_y, nullptr, s, tile_begin, tile_end);
+#define X(id, wp, i, st, mb)                                                                                      \
+    case id:                                                                                                      \
+        if (ranked)                                                                                               \
+            return fan ? launch_wmerge<wp, i, st, mb, true, true>(A, d_x, d_y, fan, s, tile_begin, tile_end)      \
+                       : launch_wmerge<wp, i, st, mb, false, true>(A, d_x, d_y, nullptr, s, tile_begin, tile_end); \
+        return fan ? launch_wmerge<wp, i, st, mb, true, false>(A, d_x, d_y, fan, s, tile_begin, tile_end)         \
+                   : launch_wmerge<wp, i, st, mb, false, false>(A, d_x, d_y, nullptr, s, tile_begin, tile_end);
         SMVP_WMERGE_CFGS(X)
 #undef X
     default:
@@ -991,15 +1058,24 @@ static int pipe_plan(smvp_csr *A)
     return SMVP_OK;
 }
 
+constexpr int PIPE_MAX_STREAMS = 4;
+// pieces alternate over this many streams per direction, so that the completion / semaphore latency between two
+// pieces on one stream (measured ~23 us each) hides behind the piece in flight on the other
+static int pipe_streams() { return env_int("SMVP_PIPE_STREAMS", 2, 1, PIPE_MAX_STREAMS); }
+
 struct PipeResources
 {
-    cudaStream_t up = nullptr, down = nullptr;
+    cudaStream_t up[PIPE_MAX_STREAMS] = {}, down[PIPE_MAX_STREAMS] = {};
     cudaEvent_t x_ready[PIPE_MAX_XCHUNKS] = {}, done[PIPE_MAX_RANGES] = {}, t0[PIPE_MAX_RANGES] = {}, t1[PIPE_MAX_RANGES] = {};
     cudaError_t create()
     {
-        cudaError_t e = cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking);
-        if (e == cudaSuccess)
-            e = cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking);
+        cudaError_t e = cudaSuccess;
+        for (int k = 0; k < PIPE_MAX_STREAMS && e == cudaSuccess; k++)
+        {
+            e = cudaStreamCreateWithFlags(&up[k], cudaStreamNonBlocking);
+            if (e == cudaSuccess)
+                e = cudaStreamCreateWithFlags(&down[k], cudaStreamNonBlocking);
+        }
         for (int c = 0; c < PIPE_MAX_XCHUNKS && e == cudaSuccess; c++)
             e = cudaEventCreateWithFlags(&x_ready[c], cudaEventDisableTiming);
         for (int c = 0; c < PIPE_MAX_RANGES && e == cudaSuccess; c++)
@@ -1026,10 +1102,13 @@ struct PipeResources
             if (t1[c])
                 cudaEventDestroy(t1[c]);
         }
-        if (up)
-            cudaStreamDestroy(up);
-        if (down)
-            cudaStreamDestroy(down);
+        for (int k = 0; k < PIPE_MAX_STREAMS; k++)
+        {
+            if (up[k])
+                cudaStreamDestroy(up[k]);
+            if (down[k])
+                cudaStreamDestroy(down[k]);
+        }
     }
 };
 
@@ -1061,7 +1140,7 @@ static int csr_mult_pipelined(smvp_csr *A, const double *x_host, double *y_host,
         A->pipe_res = fresh;
     }
     PipeResources &R = *static_cast<PipeResources *>(A->pipe_res);
-    const int NR = A->pipe_ranges, NX = pipe_xchunks();
+    const int NR = A->pipe_ranges, NX = pipe_xchunks(), NS = pipe_streams();
     const int64_t xchunk = ((ceil_div64(A->cols, NX) + 63) / 64) * 64; // entries per upload piece (512 B multiple)
     if (x_host)
     {
@@ -1069,8 +1148,8 @@ static int csr_mult_pipelined(smvp_csr *A, const double *x_host, double *y_host,
         {
             const int64_t a = (int64_t)k * xchunk, b = a + xchunk < A->cols ? a + xchunk : A->cols;
             if (b > a)
-                cudaMemcpyAsync(A->d_x + a, x_host + a, sizeof(double) * (size_t)(b - a), cudaMemcpyHostToDevice, R.up);
-            cudaEventRecord(R.x_ready[k], R.up);
+                cudaMemcpyAsync(A->d_x + a, x_host + a, sizeof(double) * (size_t)(b - a), cudaMemcpyHostToDevice, R.up[k % NS]);
+            cudaEventRecord(R.x_ready[k], R.up[k % NS]);
         }
     }
     int rc = SMVP_OK;
@@ -1082,11 +1161,8 @@ static int csr_mult_pipelined(smvp_csr *A, const double *x_host, double *y_host,
         {
             int k = (int)(((int64_t)A->pipe_xneed[c] - 1) / xchunk);
             k = k < NX ? k : NX - 1;
-            if (k > waited)
-            {
-                cudaStreamWaitEvent(0, R.x_ready[k], 0); // pieces are in stream order: k implies all before it
-                waited = k;
-            }
+            for (; waited < k; waited++) // pieces alternate over NS streams: wait for each one up to k
+                cudaStreamWaitEvent(0, R.x_ready[waited + 1], 0);
         }
         cudaEventRecord(R.t0[c], 0);
         if (A->pipe_tile[c + 1] > A->pipe_tile[c])
@@ -1095,17 +1171,21 @@ static int csr_mult_pipelined(smvp_csr *A, const double *x_host, double *y_host,
         if (y_host)
         {
             cudaEventRecord(R.done[c], 0);
-            cudaStreamWaitEvent(R.down, R.done[c], 0);
+            cudaStreamWaitEvent(R.down[c % NS], R.done[c], 0);
             const int32_t r0 = A->pipe_row[c], r1 = A->pipe_row[c + 1];
             if (r1 > r0)
-                cudaMemcpyAsync(y_host + r0, A->d_y + r0, sizeof(double) * (size_t)(r1 - r0), cudaMemcpyDeviceToHost, R.down);
+                cudaMemcpyAsync(y_host + r0, A->d_y + r0, sizeof(double) * (size_t)(r1 - r0), cudaMemcpyDeviceToHost,
+                                R.down[c % NS]);
         }
     }
-    e = cudaStreamSynchronize(R.up); // also covers a matrix that reads less than all of x
-    if (e == cudaSuccess)
-        e = cudaStreamSynchronize(0);
-    if (e == cudaSuccess)
-        e = cudaStreamSynchronize(R.down);
+    e = cudaStreamSynchronize(0);
+    for (int k = 0; k < NS; k++) // the upload streams too: a matrix may read less than all of x
+    {
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(R.up[k]);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(R.down[k]);
+    }
     if (rc != SMVP_OK)
         return rc;
     if (e != cudaSuccess)

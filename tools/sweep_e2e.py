@@ -30,8 +30,8 @@ for setting in ["off"] + args.settings.split(","):
         os.environ["SMVP_NO_OVERLAP"] = "1"
     else:
         os.environ.pop("SMVP_NO_OVERLAP", None)
-        r, xc = setting.split("x")
-        os.environ["SMVP_PIPE_RANGES"], os.environ["SMVP_PIPE_XCHUNKS"] = r, xc
+        r, xc, ns = (setting.split("x") + ["2"])[:3]
+        os.environ["SMVP_PIPE_RANGES"], os.environ["SMVP_PIPE_XCHUNKS"], os.environ["SMVP_PIPE_STREAMS"] = r, xc, ns
     ms = ctypes.c_double(0)
     for it in range(2 + args.steps):
         if it == 2:
@@ -45,5 +45,5 @@ for setting in ["off"] + args.settings.split(","):
     if ref is None:
         ref = hy.clone()
     same = bool(torch.equal(ref, hy))
-    print("ranges x pieces %-8s: %7.3f ms per call   multiply alone %.3f ms   y identical to the plain path: %s" %
+    print("ranges x pieces x streams %-10s: %7.3f ms per call   multiply alone %.3f ms   y identical to the plain path: %s" %
           (setting, wall, ms.value, same), flush=True)

@@ -35,6 +35,8 @@ def main():
     ap.add_argument("--cfgs", default="4,1,6,5")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--modes", default="0,1")
+    ap.add_argument("--hints", default="off,8192x4194304,0x4194304,8192x0,65536x8388608")
+    ap.add_argument("--no-vector", action="store_true")
     args = ap.parse_args()
     src = sdist.RmatSource(eng, args.scale, args.edge_factor << args.scale)
     M = N = src.rows
@@ -51,19 +53,28 @@ def main():
         A = eng.CsrMatrix.build_device(r, c, v, M, N, nnz)
         t_plan = timeit(lambda: A.set_x_device(x), 1)  # first call decides and builds the plan; then 3 warm + 1
         print("relabel=%s state=%d   set_x %.3f ms" % (mode, A.x_relabel, t_plan), flush=True)
-        for cfg in [int(t) for t in args.cfgs.split(",")]:
-            os.environ["SMVP_MERGE_CFG"] = str(cfg)
-            y.fill_(float("nan"))
-            ms = timeit(lambda: A.mult_device(None, y, eng.CSR_MERGE), args.steps)
-            tag = ""
-            if mode == "0":
-                y_plain[cfg] = y.clone()
-            elif cfg in y_plain:
-                tag = "bit-identical" if torch.equal(y, y_plain[cfg]) else "DIFFERS from plain"
-            print("  merge cfg %d: %8.3f ms  %8.1f GB/s  %s" % (cfg, ms, nbytes / ms / 1e6, tag), flush=True)
-        os.environ.pop("SMVP_MERGE_CFG", None)
-        ms = timeit(lambda: A.mult_device(None, y, eng.CSR_VECTOR), args.steps)
-        print("  vector     : %8.3f ms  %8.1f GB/s" % (ms, nbytes / ms / 1e6), flush=True)
+        hints = [""] if mode == "0" else args.hints.split(",")
+        for hint in hints:  # "off" | "L1xL2" in entries (ranked cache-retention hints of the relabelled kernel)
+            if hint == "off":
+                os.environ["SMVP_RANKED_HINTS"] = "0"
+            elif hint:
+                os.environ["SMVP_RANKED_HINTS"] = "1"
+                os.environ["SMVP_HOT_L1"], os.environ["SMVP_HOT_L2"] = hint.split("x")
+            for cfg in [int(t) for t in args.cfgs.split(",")]:
+                os.environ["SMVP_MERGE_CFG"] = str(cfg)
+                y.fill_(float("nan"))
+                ms = timeit(lambda: A.mult_device(None, y, eng.CSR_MERGE), args.steps)
+                tag = ""
+                if mode == "0":
+                    y_plain[cfg] = y.clone()
+                elif cfg in y_plain:
+                    tag = "bit-identical" if torch.equal(y, y_plain[cfg]) else "DIFFERS from plain"
+                print("  hints %-16s merge cfg %d: %8.3f ms  %8.1f GB/s  %s" % (hint, cfg, ms, nbytes / ms / 1e6, tag), flush=True)
+        for k in ("SMVP_MERGE_CFG", "SMVP_RANKED_HINTS", "SMVP_HOT_L1", "SMVP_HOT_L2"):
+            os.environ.pop(k, None)
+        if not args.no_vector:
+            ms = timeit(lambda: A.mult_device(None, y, eng.CSR_VECTOR), args.steps)
+            print("  vector     : %8.3f ms  %8.1f GB/s" % (ms, nbytes / ms / 1e6), flush=True)
         ms = timeit(lambda: A.mult_device(x, y, eng.CSR_MERGE), args.steps)
         print("  merge, x passed every call (permutation inside): %8.3f ms" % ms, flush=True)
         A.free()
