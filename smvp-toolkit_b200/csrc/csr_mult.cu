@@ -383,7 +383,7 @@ __device__ __forceinline__ TileView make_tile(int32_t r0, int32_t r1, int32_t t,
 // never meets a block-wide barrier: warps of a CTA drift apart freely, so while one waits for HBM
 // or for its x gathers the others walk.  Rows cut by lane boundaries are stitched with a segmented
 // warp scan (__shfl_up_sync), rows cut by tile boundaries by the fix-up kernel -- fixed order, no atomics.
-template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT, bool RANKED>
+template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT, bool RANKED, bool PHASED>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     csr_merge_warp_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_ind, const double *__restrict__ val,
                           const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int32_t rows,
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                 prod[q] = 0.0;
         }
 #else
-        if (RANKED || SMVP_PHASED_PLAIN)
+        if (RANKED || PHASED || SMVP_PHASED_PLAIN)
         {
             // three phases, pinned by volatile asm: all column indices, then every gather of the lane, then the products
             // (random columns: the loads are the latency, so all IPT of them must be in flight together)
@@ -787,14 +787,17 @@ static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
     return SMVP_OK;
 }
 
-#define SMVP_WMERGE_CFGS(X) \
-    X(0, 2, 14, 1, 16)      \
-    X(1, 2, 10, 1, 16)      \
-    X(2, 4, 14, 1, 8)       \
-    X(3, 2, 12, 1, 16)      \
-    X(4, 2, 10, 1, 14)      \
-    X(5, 2, 7, 1, 16)       \
-    X(6, 2, 9, 1, 16)
+// last column: issue the tile's column indices / x gathers / products in three pinned phases even in natural column
+// order.  Pays where the gathers are the latency (R-MAT, configuration 4: 8.11 -> 7.79 ms); on the stencil
+// configurations it costs registers (configuration 2 spills and drops from 2.90 to 3.41 ms), so it is per configuration.
+#define SMVP_WMERGE_CFGS(X)    \
+    X(0, 2, 14, 1, 16, false)  \
+    X(1, 2, 10, 1, 16, false)  \
+    X(2, 4, 14, 1, 8, false)   \
+    X(3, 2, 12, 1, 16, false)  \
+    X(4, 2, 10, 1, 14, true)   \
+    X(5, 2, 7, 1, 16, false)   \
+    X(6, 2, 9, 1, 16, false)
 
 // how much of the rank-ordered x a relabelled multiply asks L1 / L2 to retain (entries; SMVP_HOT_L1 / SMVP_HOT_L2)
 static void hot_limits(int32_t *l1, int32_t *l2)
@@ -804,13 +807,13 @@ static void hot_limits(int32_t *l1, int32_t *l2)
     *l2 = e2 && e2[0] ? atoi(e2) : (4 << 20); // 32 MB
 }
 
-template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT, bool RANKED>
+template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT, bool RANKED, bool PHASED>
 static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, const YFan *fanp, cudaStream_t s, int32_t tile_begin,
                          int32_t tile_end)
 {
     using Shape = MergeShape<32, IPT, STAGES>;
     constexpr int SMEM = WARPS * Shape::SMEM_BYTES;
-    auto kern = csr_merge_warp_kernel<WARPS, IPT, STAGES, MINB, FANOUT, RANKED>;
+    auto kern = csr_merge_warp_kernel<WARPS, IPT, STAGES, MINB, FANOUT, RANKED, PHASED>;
     int32_t hot_l1 = 0, hot_l2 = 0;
     if (RANKED)
         hot_limits(&hot_l1, &hot_l2);
@@ -846,8 +849,8 @@ static int wmerge_tile_items(int cfg)
 {
     switch (cfg)
     {
-#define X(id, wp, i, st, mb) \
-    case id:                 \
+#define X(id, wp, i, st, mb, ph) \
+    case id:                     \
         return 32 * i;
         SMVP_WMERGE_CFGS(X)
 #undef X
@@ -869,13 +872,13 @@ static int csr_mult_merge(smvp_csr *A, const double *d_x, double *d_y, const YFa
     const bool ranked = A->relabel_state == 1 && !(rh && rh[0] == '0');
     switch (cfg)
     {
-#define X(id, wp, i, st, mb)                                                                                      \
-    case id:                                                                                                      \
-        if (ranked)                                                                                               \
-            return fan ? launch_wmerge<wp, i, st, mb, true, true>(A, d_x, d_y, fan, s, tile_begin, tile_end)      \
-                       : launch_wmerge<wp, i, st, mb, false, true>(A, d_x, d_y, nullptr, s, tile_begin, tile_end); \
-        return fan ? launch_wmerge<wp, i, st, mb, true, false>(A, d_x, d_y, fan, s, tile_begin, tile_end)         \
-                   : launch_wmerge<wp, i, st, mb, false, false>(A, d_x, d_y, nullptr, s, tile_begin, tile_end);
+#define X(id, wp, i, st, mb, ph)                                                                                         \
+    case id:                                                                                                             \
+        if (ranked)                                                                                                      \
+            return fan ? launch_wmerge<wp, i, st, mb, true, true, true>(A, d_x, d_y, fan, s, tile_begin, tile_end)       \
+                       : launch_wmerge<wp, i, st, mb, false, true, true>(A, d_x, d_y, nullptr, s, tile_begin, tile_end); \
+        return fan ? launch_wmerge<wp, i, st, mb, true, false, ph>(A, d_x, d_y, fan, s, tile_begin, tile_end)            \
+                   : launch_wmerge<wp, i, st, mb, false, false, ph>(A, d_x, d_y, nullptr, s, tile_begin, tile_end);
         SMVP_WMERGE_CFGS(X)
 #undef X
     default:
@@ -1059,9 +1062,10 @@ static int pipe_plan(smvp_csr *A)
 }
 
 constexpr int PIPE_MAX_STREAMS = 4;
-// pieces alternate over this many streams per direction, so that the completion / semaphore latency between two
-// pieces on one stream (measured ~23 us each) hides behind the piece in flight on the other
-static int pipe_streams() { return env_int("SMVP_PIPE_STREAMS", 2, 1, PIPE_MAX_STREAMS); }
+// pieces may alternate over several streams per direction (SMVP_PIPE_STREAMS).  Measured on B200 (profiles/r01_logs/
+// e2e_sweep.log): one stream 10.15 ms per call, two 11.9 ms, three 13.2 ms -- concurrent pieces only share the link
+// and finish later, so one stream per direction is the default
+static int pipe_streams() { return env_int("SMVP_PIPE_STREAMS", 1, 1, PIPE_MAX_STREAMS); }
 
 struct PipeResources
 {
