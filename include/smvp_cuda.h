@@ -150,6 +150,9 @@ typedef struct smvp_tjds_info_t
     int64_t bytes_per_mult;   /* 12 nnz + 4 (ndiag+1) + 8 cols + 8 rows                         */
     int64_t device_bytes;
     int32_t launches_per_mult[2]; /* indexed by variant; includes the zero-fill of y            */
+    int32_t y_relabel;        /* multiply plan: 1 = the kernels scatter through popularity-relabelled row
+                                 indices and a last pass restores the row order of y, -1 = natural order,
+                                 0 = not decided yet (decided at the first pass)                  */
 } smvp_tjds_info_t;
 
 int smvp_csr_info(const smvp_csr *A, smvp_csr_info_t *out);

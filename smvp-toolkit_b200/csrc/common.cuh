@@ -165,4 +165,14 @@ struct smvp_tjds
     long long *acc;          // [2*rows] hi/lo integer accumulators
     int32_t *x_exp;          // [1] exponent bound of max |x|
     double *d_x, *d_y;
+    // popularity relabelling of the ROW space (csr_relabel.cu): 0 undecided, 1 in use, -1 not worth it
+    int32_t relabel_state;
+    int32_t *row_rel;        // [nnz]  rank of row_ind[j]; what the kernels scatter through when in use
+    int32_t *row_rank;       // [rows] rank of row r
+    double *y_rel;           // [rows] y in rank order (atomic variant)
 };
+namespace smvp
+{
+int tjds_relabel_plan(smvp_tjds *A, cudaStream_t s); // csr_relabel.cu
+void tjds_relabel_release(smvp_tjds *A);             // csr_relabel.cu
+} // namespace smvp

@@ -78,22 +78,20 @@ __global__ void __launch_bounds__(256) relabel_permute_x_kernel(const double *__
         x_rel[p] = __ldg(x + __ldg(x_order + p));
 }
 
-// decides (once per handle) and, if the plan is worth it, builds col_rel / x_order / x_rel.  Synchronous.
-int csr_relabel_plan(smvp_csr *A, cudaStream_t s)
+// Popularity order of an index space: d_idx[nnz] holds indices in [0, n).  forced > 0 builds the order whatever the
+// distribution; forced == 0 builds it only when the index space is large and skewed enough (see the header).
+// On success with *use = 1: (*d_order)[p] = index with rank p, (*d_rank)[i] = rank of index i (caller frees both).
+// Synchronous.
+int popularity_plan(const int32_t *d_idx, int64_t nnz, int32_t n, int forced, int32_t **d_order, int32_t **d_rank, int *use,
+                    cudaStream_t s)
 {
-    if (A->relabel_state != 0)
+    *use = 0;
+    *d_order = *d_rank = nullptr;
+    if (forced < 0 || nnz == 0 || n == 0 || (forced == 0 && n < RELABEL_MIN_COLS))
         return SMVP_OK;
-    const char *env = getenv("SMVP_CSR_RELABEL");
-    const int forced = (env && env[0] == '1') ? 1 : (env && env[0] == '0') ? -1 : 0;
-    const int32_t cols = A->cols;
-    if (forced < 0 || A->nnz == 0 || cols == 0 || (forced == 0 && cols < RELABEL_MIN_COLS))
-    {
-        A->relabel_state = -1;
-        return SMVP_OK;
-    }
     uint32_t *count = nullptr, *d_max = nullptr, *key_a = nullptr, *key_b = nullptr, *idx_a = nullptr, *idx_b = nullptr;
     unsigned long long *d_cover = nullptr;
-    int32_t *rank = nullptr;
+    int32_t *order = nullptr, *rank = nullptr;
     auto cleanup = [&]() {
         cudaFree(count);
         cudaFree(d_max);
@@ -102,67 +100,153 @@ int csr_relabel_plan(smvp_csr *A, cudaStream_t s)
         cudaFree(idx_a);
         cudaFree(idx_b);
         cudaFree(d_cover);
-        cudaFree(rank);
     };
     auto body = [&]() -> int {
-        const unsigned cblocks = (unsigned)ceil_div64(cols, 256);
-        SMVP_CUDA(dev_alloc(&count, (int64_t)cols + 1));
+        const unsigned cblocks = (unsigned)ceil_div64(n, 256);
+        SMVP_CUDA(dev_alloc(&count, (int64_t)n + 1));
         SMVP_CUDA(dev_alloc(&d_max, 1));
         SMVP_CUDA(dev_alloc(&d_cover, 1));
-        SMVP_CUDA(dev_alloc(&key_a, cols));
-        SMVP_CUDA(dev_alloc(&key_b, cols));
-        SMVP_CUDA(dev_alloc(&idx_a, cols));
-        SMVP_CUDA(dev_alloc(&idx_b, cols));
-        SMVP_TRY(histogram_i32(A->col_ind, A->nnz, count, (int64_t)cols + 1, s));
-        SMVP_TRY(max_u32(count, cols, d_max, s));
+        SMVP_CUDA(dev_alloc(&key_a, n));
+        SMVP_CUDA(dev_alloc(&key_b, n));
+        SMVP_CUDA(dev_alloc(&idx_a, n));
+        SMVP_CUDA(dev_alloc(&idx_b, n));
+        SMVP_TRY(histogram_i32(d_idx, nnz, count, (int64_t)n + 1, s));
+        SMVP_TRY(max_u32(count, n, d_max, s));
         uint32_t maxc = 0;
         SMVP_CUDA(cudaMemcpyAsync(&maxc, d_max, sizeof(maxc), cudaMemcpyDeviceToHost, s));
         SMVP_CUDA(cudaStreamSynchronize(s));
-        SMVP_LAUNCH(relabel_key_kernel, cblocks, 256, 0, s, (const uint32_t *)count, cols, maxc, key_a, idx_a);
+        SMVP_LAUNCH(relabel_key_kernel, cblocks, 256, 0, s, (const uint32_t *)count, n, maxc, key_a, idx_a);
         uint32_t *rk = nullptr, *ri = nullptr;
         const int lo = 0, hi = bits_for(maxc + 1u);
-        SMVP_TRY(radix_sort_pairs<uint32_t>(key_a, idx_a, key_b, idx_b, cols, &lo, &hi, 1, &rk, &ri, s));
+        SMVP_TRY(radix_sort_pairs<uint32_t>(key_a, idx_a, key_b, idx_b, n, &lo, &hi, 1, &rk, &ri, s));
         if (forced == 0)
         {
-            const int32_t k = (int32_t)(cols < RELABEL_HOT_COLS ? cols : RELABEL_HOT_COLS);
+            const int32_t k = (int32_t)(n < RELABEL_HOT_COLS ? n : RELABEL_HOT_COLS);
             SMVP_CUDA(cudaMemsetAsync(d_cover, 0, sizeof(unsigned long long), s));
             SMVP_LAUNCH(relabel_cover_kernel, (unsigned)device_props().sms * 8, 256, 0, s, (const uint32_t *)rk, k, maxc, d_cover);
             unsigned long long cover = 0;
             SMVP_CUDA(cudaMemcpyAsync(&cover, d_cover, sizeof(cover), cudaMemcpyDeviceToHost, s));
             SMVP_CUDA(cudaStreamSynchronize(s));
-            const double share = (double)cover / (double)A->nnz, fair = (double)k / (double)cols;
+            const double share = (double)cover / (double)nnz, fair = (double)k / (double)n;
             if (!(share >= 0.5 && share >= 4.0 * fair))
-            {
-                A->relabel_state = -1;
                 return SMVP_OK;
-            }
         }
-        SMVP_CUDA(dev_alloc(&rank, cols));
-        SMVP_CUDA(dev_alloc(&A->x_order, cols));
-        SMVP_CUDA(dev_alloc(&A->x_rel, cols));
-        SMVP_CUDA(dev_alloc(&A->col_rel, A->nnz));
-        SMVP_LAUNCH(relabel_rank_kernel, cblocks, 256, 0, s, (const uint32_t *)ri, cols, A->x_order, rank);
-        int64_t blocks = ceil_div64(A->nnz, 256 * 4);
-        const int64_t cap = (int64_t)device_props().sms * 16;
-        SMVP_LAUNCH(relabel_cols_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, s, (const int32_t *)A->col_ind, A->nnz,
-                    (const int32_t *)rank, A->col_rel);
+        SMVP_CUDA(dev_alloc(&order, n));
+        SMVP_CUDA(dev_alloc(&rank, n));
+        SMVP_LAUNCH(relabel_rank_kernel, cblocks, 256, 0, s, (const uint32_t *)ri, n, order, rank);
         SMVP_CUDA(cudaStreamSynchronize(s));
         SMVP_CUDA(cudaGetLastError());
-        A->device_bytes += 4 * A->nnz + 12 * (int64_t)cols;
-        A->relabel_state = 1;
+        *use = 1;
         return SMVP_OK;
     };
     const int rc = body();
     cleanup();
+    if (rc != SMVP_OK || !*use)
+    {
+        cudaFree(order);
+        cudaFree(rank);
+        *use = 0;
+        return rc;
+    }
+    *d_order = order;
+    *d_rank = rank;
+    return SMVP_OK;
+}
+
+// out[j] = rank[idx[j]] (asynchronous on s)
+int relabel_indices(const int32_t *d_idx, int64_t nnz, const int32_t *d_rank, int32_t *d_out, cudaStream_t s)
+{
+    if (nnz > 0)
+    {
+        int64_t blocks = ceil_div64(nnz, 256 * 4);
+        const int64_t cap = (int64_t)device_props().sms * 16;
+        SMVP_LAUNCH(relabel_cols_kernel, (unsigned)(blocks < cap ? blocks : cap), 256, 0, s, d_idx, nnz, d_rank, d_out);
+        SMVP_CUDA(cudaGetLastError());
+    }
+    return SMVP_OK;
+}
+
+static int env_forced(const char *name)
+{
+    const char *env = getenv(name);
+    return (env && env[0] == '1') ? 1 : (env && env[0] == '0') ? -1 : 0;
+}
+
+// decides (once per handle) and, if the plan is worth it, builds col_rel / x_order / x_rel.  Synchronous.
+int csr_relabel_plan(smvp_csr *A, cudaStream_t s)
+{
+    if (A->relabel_state != 0)
+        return SMVP_OK;
+    int use = 0;
+    int32_t *order = nullptr, *rank = nullptr;
+    SMVP_TRY(popularity_plan(A->col_ind, A->nnz, A->cols, env_forced("SMVP_CSR_RELABEL"), &order, &rank, &use, s));
+    if (!use)
+    {
+        A->relabel_state = -1;
+        return SMVP_OK;
+    }
+    A->x_order = order;
+    auto body = [&]() -> int {
+        SMVP_CUDA(dev_alloc(&A->x_rel, A->cols));
+        SMVP_CUDA(dev_alloc(&A->col_rel, A->nnz));
+        SMVP_TRY(relabel_indices(A->col_ind, A->nnz, rank, A->col_rel, s));
+        SMVP_CUDA(cudaStreamSynchronize(s));
+        return SMVP_OK;
+    };
+    const int rc = body();
+    cudaFree(rank);
     if (rc != SMVP_OK)
     {
-        cudaFree(A->x_order);
-        cudaFree(A->x_rel);
-        cudaFree(A->col_rel);
-        A->x_order = A->col_rel = nullptr;
-        A->x_rel = nullptr;
+        csr_relabel_release(A);
+        return rc;
     }
-    return rc;
+    A->device_bytes += 4 * A->nnz + 12 * (int64_t)A->cols;
+    A->relabel_state = 1;
+    return SMVP_OK;
+}
+
+// the same for the ROWS of a TJDS handle: the multiply scatters into y[row_ind[j]], and on a power-law matrix whose
+// y exceeds L2 those read-modify-writes miss the way the CSR gathers do.  row_rel replaces row_ind in the kernels,
+// the sums land in rank order and one last pass puts them back: y[r] = y_rel[row_rank[r]].
+int tjds_relabel_plan(smvp_tjds *A, cudaStream_t s)
+{
+    if (A->relabel_state != 0)
+        return SMVP_OK;
+    int use = 0;
+    int32_t *order = nullptr, *rank = nullptr;
+    SMVP_TRY(popularity_plan(A->row_ind, A->nnz, A->rows, env_forced("SMVP_TJDS_RELABEL"), &order, &rank, &use, s));
+    if (!use)
+    {
+        A->relabel_state = -1;
+        return SMVP_OK;
+    }
+    cudaFree(order);
+    A->row_rank = rank;
+    auto body = [&]() -> int {
+        SMVP_CUDA(dev_alloc(&A->y_rel, A->rows));
+        SMVP_CUDA(dev_alloc(&A->row_rel, A->nnz));
+        SMVP_TRY(relabel_indices(A->row_ind, A->nnz, rank, A->row_rel, s));
+        SMVP_CUDA(cudaStreamSynchronize(s));
+        return SMVP_OK;
+    };
+    const int rc = body();
+    if (rc != SMVP_OK)
+    {
+        tjds_relabel_release(A);
+        return rc;
+    }
+    A->device_bytes += 4 * A->nnz + 12 * (int64_t)A->rows;
+    A->relabel_state = 1;
+    return SMVP_OK;
+}
+
+void tjds_relabel_release(smvp_tjds *A)
+{
+    cudaFree(A->row_rank);
+    cudaFree(A->row_rel);
+    cudaFree(A->y_rel);
+    A->row_rank = A->row_rel = nullptr;
+    A->y_rel = nullptr;
 }
 
 // x_rel = x in rank order (asynchronous on s)

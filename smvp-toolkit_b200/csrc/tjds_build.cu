@@ -98,6 +98,7 @@ void tjds_release(smvp_tjds *A)
     cudaFree(A->x_exp);
     cudaFree(A->d_x);
     cudaFree(A->d_y);
+    tjds_relabel_release(A);
     delete A;
 }
 

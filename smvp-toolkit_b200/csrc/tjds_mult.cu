@@ -260,12 +260,15 @@ __global__ void __launch_bounds__(256) tjds_det_kernel(const int2 *__restrict__ 
     }
 }
 
+// row_rank != NULL: the accumulators and row_exp are in popularity-rank order (relabelled handle), y is not
 __global__ void __launch_bounds__(256) tjds_det_finalize_kernel(const long long *__restrict__ acc, const int32_t *__restrict__ row_exp,
-                                                                const int32_t *__restrict__ x_exp, int32_t rows, double *__restrict__ y)
+                                                                const int32_t *__restrict__ x_exp, int32_t rows, double *__restrict__ y,
+                                                                const int32_t *__restrict__ row_rank)
 {
-    const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rows)
+    const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows)
         return;
+    const int32_t r = row_rank ? row_rank[row] : row;
     longlong2 a;
     a.x = acc[r];
     a.y = acc[(int64_t)rows + r];
@@ -277,8 +280,19 @@ __global__ void __launch_bounds__(256) tjds_det_finalize_kernel(const long long 
         const int32_t T = row_exp[r] + *x_exp;
         out = scalbn(s, T - TJDS_FRAC);
     }
-    y[r] = out;
+    y[row] = out;
 }
+
+// y[r] = y_rel[rank[r]]: the atomic variant of a relabelled handle sums in rank order
+__global__ void __launch_bounds__(256) tjds_unrank_y_kernel(const double *__restrict__ y_rel, const int32_t *__restrict__ row_rank,
+                                                            int32_t rows, double *__restrict__ y)
+{
+    for (int32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x)
+        y[r] = __ldg(y_rel + __ldg(row_rank + r));
+}
+
+// the row indices the kernels scatter through: the relabelled copy when that plan is in use (csr_relabel.cu)
+static inline const int32_t *mult_rows(const smvp_tjds *A) { return A->relabel_state == 1 ? A->row_rel : A->row_ind; }
 
 static int tjds_plan(smvp_tjds *A, cudaStream_t s)
 {
@@ -321,8 +335,8 @@ static int tjds_prepare_det(smvp_tjds *A, cudaStream_t s)
         const int64_t cap = (int64_t)device_props().sms * 16;
         if (blocks > cap)
             blocks = cap;
-        SMVP_LAUNCH(tjds_row_bound_kernel, (unsigned)blocks, 256, 0, s, (const int32_t *)A->row_ind, (const double *)A->val, A->nnz,
-                    A->row_exp, cnt);
+        SMVP_LAUNCH(tjds_row_bound_kernel, (unsigned)blocks, 256, 0, s, mult_rows(A), (const double *)A->val, A->nnz,
+                    A->row_exp, cnt); // after the relabel decision: row_exp lives in the index space the kernels use
     }
     if (A->rows > 0)
         SMVP_LAUNCH(tjds_row_exp_kernel, (unsigned)ceil_div64(A->rows, 256), 256, 0, s, A->row_exp, (const uint32_t *)cnt, A->rows);
@@ -380,9 +394,14 @@ extern "C" int smvp_tjds_mult_device(smvp_tjds *A, double *d_y, int variant, int
     cudaStream_t s = (cudaStream_t)stream;
     const int32_t lim = tjds_effective_limit(A, diag_limit);
     SMVP_TRY(tjds_plan(A, s));
+    SMVP_TRY(tjds_relabel_plan(A, s));
+    const bool ranked = A->relabel_state == 1;
     const unsigned blocks = (unsigned)A->num_seg_blocks;
     if (variant == SMVP_TJDS_ATOMIC)
     {
+        double *y_caller = d_y;
+        if (ranked)
+            d_y = A->y_rel; // sums land in rank order; tjds_unrank_y_kernel puts them back
         SMVP_CUDA(cudaMemsetAsync(d_y, 0, sizeof(double) * (size_t)A->rows, s));
         if (blocks > 0 && lim > 0)
         {
@@ -390,13 +409,20 @@ extern "C" int smvp_tjds_mult_device(smvp_tjds *A, double *d_y, int variant, int
             const int unroll = ue && ue[0] ? atoi(ue) : 4;
             if (unroll == 8)
                 SMVP_LAUNCH(tjds_atomic_kernel<8>, blocks, 256, 0, s, (const int2 *)A->seg_blocks, (const int32_t *)A->start_pos, (const int32_t *)A->slot_len,
-                        (const int32_t *)A->row_ind, (const double *)A->val, (const double *)A->x_perm, d_y, A->nslots, lim);
+                        mult_rows(A), (const double *)A->val, (const double *)A->x_perm, d_y, A->nslots, lim);
             else if (unroll == 2)
                 SMVP_LAUNCH(tjds_atomic_kernel<2>, blocks, 256, 0, s, (const int2 *)A->seg_blocks, (const int32_t *)A->start_pos, (const int32_t *)A->slot_len,
-                        (const int32_t *)A->row_ind, (const double *)A->val, (const double *)A->x_perm, d_y, A->nslots, lim);
+                        mult_rows(A), (const double *)A->val, (const double *)A->x_perm, d_y, A->nslots, lim);
             else
                 SMVP_LAUNCH(tjds_atomic_kernel<4>, blocks, 256, 0, s, (const int2 *)A->seg_blocks, (const int32_t *)A->start_pos, (const int32_t *)A->slot_len,
-                        (const int32_t *)A->row_ind, (const double *)A->val, (const double *)A->x_perm, d_y, A->nslots, lim);
+                        mult_rows(A), (const double *)A->val, (const double *)A->x_perm, d_y, A->nslots, lim);
+        }
+        if (ranked)
+        {
+            int64_t ub = ceil_div64(A->rows, 256 * 4);
+            const int64_t cap = (int64_t)device_props().sms * 8;
+            SMVP_LAUNCH(tjds_unrank_y_kernel, (unsigned)(ub < cap ? ub : cap), 256, 0, s, (const double *)A->y_rel,
+                        (const int32_t *)A->row_rank, A->rows, y_caller);
         }
     }
     else
@@ -405,10 +431,11 @@ extern "C" int smvp_tjds_mult_device(smvp_tjds *A, double *d_y, int variant, int
         SMVP_CUDA(cudaMemsetAsync(A->acc, 0, sizeof(long long) * 2 * (size_t)A->rows, s));
         if (blocks > 0 && lim > 0)
             SMVP_LAUNCH(tjds_det_kernel<4>, blocks, 256, 0, s, (const int2 *)A->seg_blocks, (const int32_t *)A->start_pos, (const int32_t *)A->slot_len,
-                        (const int32_t *)A->row_ind, (const double *)A->val, (const double *)A->x_perm, (const int32_t *)A->row_exp,
+                        mult_rows(A), (const double *)A->val, (const double *)A->x_perm, (const int32_t *)A->row_exp,
                         (const int32_t *)A->x_exp, (unsigned long long *)A->acc, A->rows, A->nslots, lim);
         SMVP_LAUNCH(tjds_det_finalize_kernel, (unsigned)ceil_div64(A->rows, 256), 256, 0, s, (const long long *)A->acc,
-                    (const int32_t *)A->row_exp, (const int32_t *)A->x_exp, A->rows, d_y);
+                    (const int32_t *)A->row_exp, (const int32_t *)A->x_exp, A->rows, d_y,
+                    ranked ? (const int32_t *)A->row_rank : nullptr);
     }
     SMVP_CUDA(cudaGetLastError());
     return SMVP_OK;
@@ -430,6 +457,8 @@ extern "C" int smvp_tjds_mult(smvp_tjds *A, const double *x_host, double *y_host
     // x is permuted once, before the loop, as the reference does at build time (main-cli.c:907-923)
     SMVP_TRY(smvp_tjds_set_x_device(A, A->d_x, nullptr));
     SMVP_TRY(tjds_plan(A, 0));
+    if (A->rows > 0)
+        SMVP_TRY(tjds_relabel_plan(A, 0));
     if (variant == SMVP_TJDS_DETERMINISTIC && A->rows > 0)
         SMVP_TRY(tjds_prepare_det(A, 0));
     cudaEvent_t e0, e1;
@@ -477,7 +506,8 @@ extern "C" int smvp_tjds_info(const smvp_tjds *A, smvp_tjds_info_t *out)
     out->input_order = A->input_order;
     out->bytes_per_mult = 12 * A->nnz + 4 * ((int64_t)A->ndiag + 1) + 8 * (int64_t)A->cols + 8 * (int64_t)A->rows;
     out->device_bytes = A->device_bytes;
-    out->launches_per_mult[SMVP_TJDS_ATOMIC] = 1;
+    out->launches_per_mult[SMVP_TJDS_ATOMIC] = A->relabel_state == 1 ? 2 : 1;
     out->launches_per_mult[SMVP_TJDS_DETERMINISTIC] = 2;
+    out->y_relabel = A->relabel_state;
     return SMVP_OK;
 }

@@ -50,7 +50,7 @@ class _CsrInfo(ctypes.Structure):
 class _TjdsInfo(ctypes.Structure):
     _fields_ = [("rows", ctypes.c_int32), ("cols", ctypes.c_int32), ("nnz", ctypes.c_int64), ("ndiag", ctypes.c_int32),
                 ("ref_diag_limit", ctypes.c_int32), ("input_order", ctypes.c_int32), ("bytes_per_mult", ctypes.c_int64),
-                ("device_bytes", ctypes.c_int64), ("launches_per_mult", ctypes.c_int32 * 2)]
+                ("device_bytes", ctypes.c_int64), ("launches_per_mult", ctypes.c_int32 * 2), ("y_relabel", ctypes.c_int32)]
 
 
 class _TimeStats(ctypes.Structure):
@@ -298,6 +298,13 @@ class TjdsMatrix:
         self.ref_diag_limit, self.input_order = info.ref_diag_limit, info.input_order
         self.bytes_per_mult, self.device_bytes = info.bytes_per_mult, info.device_bytes
         self.launches_per_mult = list(info.launches_per_mult)
+
+    @property
+    def y_relabel(self):
+        """1: the multiply scatters through popularity-relabelled rows, -1: natural order, 0: not decided yet."""
+        info = _TjdsInfo()
+        _check(lib().smvp_tjds_info(self._h, ctypes.byref(info)), "smvp_tjds_info")
+        return info.y_relabel
 
     @classmethod
     def build(cls, coo, rows, cols):

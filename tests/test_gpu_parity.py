@@ -419,6 +419,38 @@ def test_csr_relabel_auto_decision(eng):
         A.free()
 
 
+def test_tjds_relabel_forced(eng, monkeypatch):
+    """Row-space relabelling of TJDS (the scatter side of the same plan): exported arrays unchanged, atomic variant
+    within 1e-12, deterministic variant bit-identical to the natural-order handle, reference-compatible diagonal
+    limit still honoured."""
+    rng = np.random.default_rng(79)
+    m, n = 40009, 30011
+    coo_t = _powerlaw_coo(rng, n, m, 500000, 4.0)  # power law over the ROWS: build it transposed
+    coo = oracle.make_coo(coo_t["col"], coo_t["row"], coo_t["val"])
+    x = rng.uniform(-1, 1, n)
+    t = oracle.tjds_build(coo, m, n)
+    y_ref = oracle.csr_mult(*oracle.csr_build(coo, m, n), x)
+    monkeypatch.setenv("SMVP_TJDS_RELABEL", "0")
+    P = eng.TjdsMatrix.build(coo, m, n)
+    y_det_plain, _ = P.mult(x, iters=1, variant=eng.TJDS_DETERMINISTIC)
+    y_lim_plain, _ = P.mult(x, iters=1, variant=eng.TJDS_DETERMINISTIC, diag_limit=P.ref_diag_limit)
+    assert P.y_relabel == -1
+    monkeypatch.setenv("SMVP_TJDS_RELABEL", "1")
+    A = eng.TjdsMatrix.build(coo, m, n)
+    y_at, _ = A.mult(x, iters=2, variant=eng.TJDS_ATOMIC)
+    assert A.y_relabel == 1
+    assert util.rel_l2(y_at, y_ref) <= TOL
+    y_det, _ = A.mult(x, iters=2, variant=eng.TJDS_DETERMINISTIC)
+    assert util.rel_l2(y_det, y_ref) <= TOL
+    assert np.array_equal(y_det.view(np.int64), y_det_plain.view(np.int64))
+    y_lim, _ = A.mult(x, iters=1, variant=eng.TJDS_DETERMINISTIC, diag_limit=A.ref_diag_limit)
+    assert np.array_equal(y_lim.view(np.int64), y_lim_plain.view(np.int64))
+    perm, sp, ri, va = A.export()
+    assert np.array_equal(perm, t.perm) and np.array_equal(sp, t.start_pos) and np.array_equal(ri, t.row_ind)
+    A.free()
+    P.free()
+
+
 def test_fanout_and_write_only_y(eng):
     """smvp_csr_mult_device_fanout: one pass stores y into several destinations (the fused multi-GPU exchange writes
     peers' buffers this way); every destination must equal the plain result, for both kernels."""
