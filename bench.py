@@ -369,7 +369,7 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, {"rows": M, "cols": N, "nnz": nnz_total, "bytes_per_spmv": nbytes,
                                              "partition": op.partition_desc, "kernel_variant": op.variant_name,
-                                             "build_s": build_s}),
+                                             "build_s": build_s, "multiply_plan": op.plan_desc()}),
             "gflops": 2 * nnz_total / (ms_per_step * 1e-3) / 1e9,
             "pct_of_hbm_peak_8000": 100.0 * value / 8000.0 / world,
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),

@@ -427,6 +427,15 @@ class RowBlockCsr:
     def measured_traffic_bytes(self):
         return _measured_traffic(self.kernel_name)
 
+    def plan_desc(self):
+        """What the multiply does beyond the plain kernel (decided by the library from the matrix, reported as is)."""
+        if self.A.x_relabel == 1:
+            return ("column space relabelled by popularity (smvp_csr_info_t.x_relabel = 1): the kernels read rank-ordered "
+                    "column indices and a permuted copy of x formed ONCE per x by smvp_csr_set_x_device, outside the "
+                    "steps -- x is constant over the -n loop, the reference permutes x once for TJDS the same way "
+                    "(main-cli.c:907-923); e2e pays the permutation every step")
+        return "natural column order"
+
     def free(self):
         for A in self.subs:
             A.free()
@@ -473,6 +482,12 @@ class ColBlockTjds:
         self.e2e_api = ("smvp_tjds_mult(A, x_host, y_host, iters=1) [C ABI, pinned host buffers]" if world == 1 else
                         "H2D x slice -> smvp_tjds_set_x_device + smvp_tjds_mult_device -> NCCL reduce-scatter -> D2H y block")
         self.x = None
+
+    def plan_desc(self):
+        if self.T.y_relabel == 1:
+            return ("row space relabelled by popularity (smvp_tjds_info_t.y_relabel = 1): the kernels scatter through "
+                    "rank-ordered row indices, a last pass inside every step restores the row order of y")
+        return "natural row order"
 
     def set_x(self, x, stream=None):
         self.x = x
