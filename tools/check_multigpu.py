@@ -32,6 +32,8 @@ def main():
         torch.cuda.synchronize()
         y_ref = whole.y_full.clone()
         nrm = float(torch.linalg.norm(y_ref))
+        # the sharded R-MAT operators run with the popularity relabelling forced on (small matrices never choose it)
+        os.environ["SMVP_CSR_RELABEL"] = "1" if kind == "rmat" else "0"
         for exch in ("nccl", "multicast", "p2p", "copy", "pipeline"):
             for variant in (eng.CSR_VECTOR, eng.CSR_MERGE):
                 try:
@@ -50,8 +52,8 @@ def main():
                 err = float(torch.linalg.norm(op.y_full - y_ref)) / nrm
                 ok = err <= 1e-12
                 fails += 0 if ok else 1
-                print("rank %d %-7s csr %-9s variant %d rows [%d,%d): rel_l2 %.2e %s" % (
-                    rank, kind, exch, variant, op.r0, op.r1, err, "ok" if ok else "FAIL"), flush=True)
+                print("rank %d %-7s csr %-9s variant %d rows [%d,%d) x_relabel %d: rel_l2 %.2e %s" % (
+                    rank, kind, exch, variant, op.r0, op.r1, op.A.x_relabel, err, "ok" if ok else "FAIL"), flush=True)
                 op.free()
                 del op
         if kind == "stencil":
