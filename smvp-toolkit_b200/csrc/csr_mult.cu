@@ -92,15 +92,21 @@ __device__ __forceinline__ double ldg_x_ranked(const double *x, int32_t c, int32
     double v;
     const uint64_t pol = c < hot_l2 ? pol_last : pol_first;
     if (c < hot_l1)
-        asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(x + c), "l"(pol));
+        asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %2, 8, %1;\n\tld.global.nc.L1::evict_last.L2::cache_hint.f64 %0, [a], %3;\n\t}"
+                     : "=d"(v)
+                     : "l"(x), "r"(c), "l"(pol));
     else
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(x + c), "l"(pol));
+        asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %2, 8, %1;\n\tld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [a], %3;\n\t}"
+                     : "=d"(v)
+                     : "l"(x), "r"(c), "l"(pol));
     return v;
 }
-__device__ __forceinline__ double ldg_x_pinned(const double *p) // plain read-only load whose position in the code is kept
+// x[c] through the read-only path; the address is formed inside the asm (one IMAD.WIDE -- left to the compiler, the
+// predicated index select turns it into a four-instruction sign-extend / shift sequence) and the load keeps its place
+__device__ __forceinline__ double ldg_x_pinned(const double *x, int32_t c)
 {
     double v;
-    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %2, 8, %1;\n\tld.global.nc.f64 %0, [a];\n\t}" : "=d"(v) : "l"(x), "r"(c));
     return v;
 }
 __device__ __forceinline__ uint64_t l2_evict_first_policy()
@@ -121,22 +127,16 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
 // Tuning switches, A/B-tested on B200 (profiles/r01_logs/ab_variants.log, stencil 369^3, ms per SpMV):
 //   all off 2.995 | explicit 32-bit ld.shared 2.984 | + warp-uniform fast path for regular tiles 3.13 |
 //   + clamped (unpredicated) gathers 3.20 | + early-exit stitch scan 3.26 | all on 3.22
-// i.e. the kernel is latency- not instruction-bound: every extra vote / branch costs more than the
-// instructions it saves.  The defaults are the measured winner; the others stay for future re-tests.
+// i.e. every extra vote / branch costs more than the instructions it saves.  The fast path and the clamped gathers
+// have since been removed from the source; the others stay for future re-tests.
 #ifndef SMVP_ASM_LDS
 #define SMVP_ASM_LDS 1
-#endif
-#ifndef SMVP_CLAMP_GATHER
-#define SMVP_CLAMP_GATHER 0
-#endif
-#ifndef SMVP_FAST_PATH
-#define SMVP_FAST_PATH 0
 #endif
 #ifndef SMVP_SCAN_EXIT
 #define SMVP_SCAN_EXIT 0
 #endif
-#ifndef SMVP_PHASED_PLAIN
-#define SMVP_PHASED_PLAIN 0 // natural-order matrices: issue indices / gathers / products in three pinned phases too
+#ifndef SMVP_PIN_BASES
+#define SMVP_PIN_BASES 0 // pin the lane's two shared-window bases in registers (fewer instructions, but the 14-item configurations spill)
 #endif
 #ifndef SMVP_X_EVICT_LAST
 #define SMVP_X_EVICT_LAST 0 // gather x with an L2 evict-last policy: measured 1 % on the stencil, 0 % on R-MAT -> off
@@ -383,7 +383,7 @@ __device__ __forceinline__ TileView make_tile(int32_t r0, int32_t r1, int32_t t,
 // never meets a block-wide barrier: warps of a CTA drift apart freely, so while one waits for HBM
 // or for its x gathers the others walk.  Rows cut by lane boundaries are stitched with a segmented
 // warp scan (__shfl_up_sync), rows cut by tile boundaries by the fix-up kernel -- fixed order, no atomics.
-template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT, bool RANKED, bool PHASED>
+template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT, bool RANKED>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     csr_merge_warp_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_ind, const double *__restrict__ val,
                           const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int32_t rows,
@@ -396,7 +396,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     extern __shared__ __align__(128) unsigned char stage_mem[];
     __shared__ __align__(8) uint64_t full_bar[WARPS];
 
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // the warp index and the tile coordinates below are broadcast from lane 0: the values are the same in every lane
+    // anyway, but the broadcast lets the compiler PROVE it and keep the whole tile bookkeeping (and the operands of the
+    // bulk copies) in uniform registers instead of electing a lane and converting per copy
+    const int lane = threadIdx.x & 31, w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int64_t total = (int64_t)rows + nnz;
     unsigned char *base = stage_mem + (size_t)w * Shape::SMEM_BYTES;
     uint64_t *my_bar = &full_bar[w];
@@ -433,8 +436,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     int32_t cur_r0 = 0, cur_r1 = 0; // merge coordinates of the tile in flight: the only tile state kept across the loop
     if (t < num_tiles)
     {
-        cur_r0 = __ldg(tile_row + t);
-        cur_r1 = __ldg(tile_row + t + 1);
+        cur_r0 = __shfl_sync(0xffffffffu, __ldg(tile_row + t), 0);
+        cur_r1 = __shfl_sync(0xffffffffu, __ldg(tile_row + t + 1), 0);
         if (lane == 0)
             issue(make_tile(cur_r0, cur_r1, t, Shape::TILE, total));
     }
@@ -469,7 +472,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         int32_t lo = d > nnz_t ? d - nnz_t : 0, hi = d < rows_t ? d : rows_t;
         if (lo < hi)
         {
-            int32_t g = (int32_t)(((uint32_t)d * (uint32_t)rows_t) / (uint32_t)items_t); // < 2^20: 32-bit is exact
+            // first guess by interpolation.  The divisor is the FULL tile size (a compile-time constant: multiply-shift
+            // instead of a 25-instruction integer division); only the matrix's last tile is shorter, and there the guess
+            // is merely a little low before the gallop corrects it.
+            int32_t g = (int32_t)(((uint32_t)d * (uint32_t)rows_t) / (uint32_t)Shape::TILE); // < 2^20: 32-bit is exact
             g = g < lo ? lo : (g > hi - 1 ? hi - 1 : g);
             int32_t step = 1;
             if (row_end(g) <= d - g - 1)
@@ -527,100 +533,50 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         const int32_t i_next = d_next - j_next;
         const int32_t cnt = j_next - j0;
 
-        // ---- all my gathers first: IPT independent loads in flight per lane.  Indices are clamped instead of
-        // predicated (a lane with fewer than IPT nonzeros re-reads the tile's last one and ignores the product).
+        // ---- all my gathers first, in three phases pinned by volatile asm: the column indices, then every x gather of
+        // the lane (IPT independent loads in flight together -- left alone, the compiler reuses one register pair and
+        // waits for each load before issuing the next), then the products.  The two shared-window bases of the lane
+        // are pinned in registers by an opaque move, so every shared load addresses [base + constant].
         double prod[IPT];
-#if SMVP_CLAMP_GATHER
-        if (nnz_t > 0)
         {
-            const int32_t jmax = nnz_t - 1;
-#pragma unroll
-            for (int q = 0; q < IPT; q++)
-            {
-                const uint32_t j = (uint32_t)min(j0 + q, jmax);
-                const int32_t c = lds_s32(scol + 4u * j);
-                prod[q] = __dmul_rn(lds_f64(sval + 8u * j), gather(c));
-            }
-        }
-        else
-        {
-#pragma unroll
-            for (int q = 0; q < IPT; q++)
-                prod[q] = 0.0;
-        }
-#else
-        if (RANKED || PHASED || SMVP_PHASED_PLAIN)
-        {
-            // three phases, pinned by volatile asm: all column indices, then every gather of the lane, then the products
-            // (random columns: the loads are the latency, so all IPT of them must be in flight together)
             int32_t cq[IPT];
-#pragma unroll
-            for (int q = 0; q < IPT; q++)
-                cq[q] = q < cnt ? lds_s32(scol + 4u * (uint32_t)(j0 + q)) : 0;
-#pragma unroll
-            for (int q = 0; q < IPT; q++)
-            {
-                prod[q] = 0.0;
-                if (q < cnt)
-                    prod[q] = RANKED ? ldg_x_ranked(x, cq[q], hot_l1, hot_l2, pol_last, pol_first) : ldg_x_pinned(x + cq[q]);
-            }
-#pragma unroll
-            for (int q = 0; q < IPT; q++)
-                if (q < cnt)
-                    prod[q] = __dmul_rn(lds_f64(sval + 8u * (uint32_t)(j0 + q)), prod[q]);
-        }
-        else
-        {
-#pragma unroll
-            for (int q = 0; q < IPT; q++)
-            {
-                prod[q] = 0.0;
-                if (q < cnt)
-                {
-                    const uint32_t j = (uint32_t)(j0 + q);
-                    const int32_t c = lds_s32(scol + 4u * j);
-                    prod[q] = __dmul_rn(lds_f64(sval + 8u * j), gather(c));
-                }
-            }
-        }
+            uint32_t cbase = scol + 4u * (uint32_t)j0, vbase = sval + 8u * (uint32_t)j0;
+#if SMVP_PIN_BASES
+            asm volatile("" : "+r"(cbase), "+r"(vbase));
 #endif
+            // (every slot gets a defined value: leaving the dead ones undefined makes the compiler carry the previous
+            // tile's registers through the loop and spill them)
+#pragma unroll
+            for (int q = 0; q < IPT; q++)
+                cq[q] = q < cnt ? lds_s32(cbase + 4u * q) : 0;
+#pragma unroll
+            for (int q = 0; q < IPT; q++)
+            {
+                prod[q] = 0.0;
+                if (q < cnt)
+                    prod[q] = RANKED ? ldg_x_ranked(x, cq[q], hot_l1, hot_l2, pol_last, pol_first) : ldg_x_pinned(x, cq[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < IPT; q++)
+                if (q < cnt)
+                    prod[q] = __dmul_rn(lds_f64(vbase + 8u * q), prod[q]);
+        }
 
         double sum = 0.0, first_sum = 0.0;
         bool has_first = false;
-        const int32_t nrow = i_next - i0; // row ends among my items
-        // fast path (whole warp): every lane holds either IPT nonzeros and no row end, or IPT-1 nonzeros followed
-        // by exactly one row end -- the shape of every interior tile of a regular matrix
-#if SMVP_FAST_PATH
-        const bool simple = (nrow == 0 && cnt == IPT) || (nrow == 1 && cnt == IPT - 1 && row_end(i0) == j0 + cnt);
-        const bool all_simple = __all_sync(0xffffffffu, simple);
-#else
-        const bool all_simple = false;
-        (void)nrow;
-#endif
-        if (all_simple)
         {
-#pragma unroll
-            for (int q = 0; q < IPT - 1; q++)
-                sum = __dadd_rn(sum, prod[q]);
-            if (nrow == 0)
-                sum = __dadd_rn(sum, prod[IPT - 1]);
-            else
-            {
-                has_first = true;
-                first_sum = sum;
-                sum = 0.0;
-            }
-        }
-        else
-        {
+            // Walk.  `until` = nonzeros of mine before my next row end (relative to j0, so each test is against a constant;
+            // "no further row end of mine" = never).  Dead slots (q >= cnt) hold +0.0, and a partial sum that starts at
+            // +0.0 can never become -0.0, so adding them is exact: the loop needs no "is this slot live" test, and the row
+            // ends that follow my last nonzero are flushed by the same test at the first dead slot.
             int32_t row = i0;
-            int32_t end = row < rows_t ? row_end(row) : 0x7fffffff;
+            int32_t until = (row < i_next ? row_end(row) : 0x7fffffff) - j0;
 #pragma unroll
             for (int q = 0; q < IPT; q++)
             {
-                if (q < cnt)
+                if (until <= q) // rare: a row end (or a run of empty rows) sits before item q
                 {
-                    while (end <= j0 + q)
+                    do
                     {
                         if (!has_first)
                         {
@@ -631,11 +587,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                             store_y<FANOUT>(y, fan, (int64_t)tile_r0 + row, sum);
                         sum = 0.0;
                         row++;
-                        end = row < rows_t ? row_end(row) : 0x7fffffff;
-                    }
-                    sum = __dadd_rn(sum, prod[q]);
+                        until = (row < i_next ? row_end(row) : 0x7fffffff) - j0;
+                    } while (until <= q);
                 }
+                sum = __dadd_rn(sum, prod[q]);
             }
+            // every row end of mine has at most IPT - 1 of my nonzeros before it, so the loop above has seen them all;
+            // this is only a safety net
             while (row < i_next)
             {
                 if (!has_first)
@@ -655,8 +613,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         const int32_t tn = t + warp_stride;
         if (tn < num_tiles && tn > t)
         {
-            cur_r0 = __ldg(tile_row + tn);
-            cur_r1 = __ldg(tile_row + tn + 1);
+            cur_r0 = __shfl_sync(0xffffffffu, __ldg(tile_row + tn), 0);
+            cur_r1 = __shfl_sync(0xffffffffu, __ldg(tile_row + tn + 1), 0);
             if (lane == 0)
                 issue(make_tile(cur_r0, cur_r1, tn, Shape::TILE, total));
         }
@@ -787,17 +745,14 @@ static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
     return SMVP_OK;
 }
 
-// last column: issue the tile's column indices / x gathers / products in three pinned phases even in natural column
-// order.  Pays where the gathers are the latency (R-MAT, configuration 4: 8.11 -> 7.79 ms); on the stencil
-// configurations it costs registers (configuration 2 spills and drops from 2.90 to 3.41 ms), so it is per configuration.
-#define SMVP_WMERGE_CFGS(X)    \
-    X(0, 2, 14, 1, 16, false)  \
-    X(1, 2, 10, 1, 16, false)  \
-    X(2, 4, 14, 1, 8, false)   \
-    X(3, 2, 12, 1, 16, false)  \
-    X(4, 2, 10, 1, 14, true)   \
-    X(5, 2, 7, 1, 16, false)   \
-    X(6, 2, 9, 1, 16, false)
+#define SMVP_WMERGE_CFGS(X) \
+    X(0, 2, 14, 1, 16)      \
+    X(1, 2, 10, 1, 16)      \
+    X(2, 4, 14, 1, 8)       \
+    X(3, 2, 12, 1, 16)      \
+    X(4, 2, 10, 1, 14)      \
+    X(5, 2, 7, 1, 16)       \
+    X(6, 2, 9, 1, 16)
 
 // how much of the rank-ordered x a relabelled multiply asks L1 / L2 to retain (entries; SMVP_HOT_L1 / SMVP_HOT_L2)
 static void hot_limits(int32_t *l1, int32_t *l2)
@@ -807,13 +762,13 @@ static void hot_limits(int32_t *l1, int32_t *l2)
     *l2 = e2 && e2[0] ? atoi(e2) : (4 << 20); // 32 MB
 }
 
-template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT, bool RANKED, bool PHASED>
+template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT, bool RANKED>
 static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, const YFan *fanp, cudaStream_t s, int32_t tile_begin,
                          int32_t tile_end)
 {
     using Shape = MergeShape<32, IPT, STAGES>;
     constexpr int SMEM = WARPS * Shape::SMEM_BYTES;
-    auto kern = csr_merge_warp_kernel<WARPS, IPT, STAGES, MINB, FANOUT, RANKED, PHASED>;
+    auto kern = csr_merge_warp_kernel<WARPS, IPT, STAGES, MINB, FANOUT, RANKED>;
     int32_t hot_l1 = 0, hot_l2 = 0;
     if (RANKED)
         hot_limits(&hot_l1, &hot_l2);
@@ -849,8 +804,8 @@ static int wmerge_tile_items(int cfg)
 {
     switch (cfg)
     {
-#define X(id, wp, i, st, mb, ph) \
-    case id:                     \
+#define X(id, wp, i, st, mb) \
+    case id:                 \
         return 32 * i;
         SMVP_WMERGE_CFGS(X)
 #undef X
@@ -872,13 +827,13 @@ static int csr_mult_merge(smvp_csr *A, const double *d_x, double *d_y, const YFa
     const bool ranked = A->relabel_state == 1 && !(rh && rh[0] == '0');
     switch (cfg)
     {
-#define X(id, wp, i, st, mb, ph)                                                                                         \
-    case id:                                                                                                             \
-        if (ranked)                                                                                                      \
-            return fan ? launch_wmerge<wp, i, st, mb, true, true, true>(A, d_x, d_y, fan, s, tile_begin, tile_end)       \
-                       : launch_wmerge<wp, i, st, mb, false, true, true>(A, d_x, d_y, nullptr, s, tile_begin, tile_end); \
-        return fan ? launch_wmerge<wp, i, st, mb, true, false, ph>(A, d_x, d_y, fan, s, tile_begin, tile_end)            \
-                   : launch_wmerge<wp, i, st, mb, false, false, ph>(A, d_x, d_y, nullptr, s, tile_begin, tile_end);
+#define X(id, wp, i, st, mb)                                                                                       \
+    case id:                                                                                                       \
+        if (ranked)                                                                                                \
+            return fan ? launch_wmerge<wp, i, st, mb, true, true>(A, d_x, d_y, fan, s, tile_begin, tile_end)       \
+                       : launch_wmerge<wp, i, st, mb, false, true>(A, d_x, d_y, nullptr, s, tile_begin, tile_end); \
+        return fan ? launch_wmerge<wp, i, st, mb, true, false>(A, d_x, d_y, fan, s, tile_begin, tile_end)          \
+                   : launch_wmerge<wp, i, st, mb, false, false>(A, d_x, d_y, nullptr, s, tile_begin, tile_end);
         SMVP_WMERGE_CFGS(X)
 #undef X
     default:

@@ -332,6 +332,35 @@ def test_host_call_pipelined_transfers(eng, monkeypatch, banded):
     A.free()
 
 
+def test_host_call_pipelined_degenerate_shapes(eng):
+    """Shapes on which the pipelined host pass has little to pipeline: a tall matrix with 3 columns (x is one upload
+    piece), a wide one with 4 rows (one tile range holds everything, the others are empty), a big matrix without a
+    single nonzero (no range reads x), and one whose FIRST row already reads the last column (every range waits
+    for all of x)."""
+    rng = np.random.default_rng(41)
+    big = (1 << 21) + 777
+    cases = []
+    r = np.arange(big, dtype=np.int64)
+    cases.append((big, 3, r, r % 3))                                              # tall
+    c = np.sort(rng.choice(big, size=300000, replace=False))
+    cases.append((4, big, rng.integers(0, 4, len(c)), c))                         # wide
+    cases.append((big, big, np.zeros(0, np.int64), np.zeros(0, np.int64)))        # empty
+    cases.append((big, big, np.concatenate([[0], r]), np.concatenate([[big - 1], np.maximum(r - 1, 0)])))  # first row reaches the end
+    for m, n, rows, cols in cases:
+        key = np.unique(np.asarray(rows, np.int64) * n + np.asarray(cols, np.int64))
+        coo = oracle.make_coo(key // n, key % n, rng.uniform(-1, 1, len(key)))
+        x = rng.uniform(-1, 1, n)
+        y_ref = oracle.csr_mult(*oracle.csr_build(coo, m, n), x)
+        A = eng.CsrMatrix.build(coo, m, n)
+        for iters in (1, 2):
+            y, td = A.mult(x, iters=iters, variant=eng.CSR_MERGE)
+            assert util.rel_l2(y, y_ref) <= TOL, (m, n, iters)
+            assert y.shape == (m,) and len(td.time_each) == iters
+            if len(key) == 0:
+                assert not y.any()
+        A.free()
+
+
 def _powerlaw_coo(rng, m, n, nnz, power):
     """Unique (row, col) pairs whose columns follow a power law spread over the whole index range (the hot columns
     are scattered by a multiplicative hash, as in an R-MAT matrix, not contiguous)."""
