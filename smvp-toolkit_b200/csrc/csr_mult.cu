@@ -91,14 +91,11 @@ __device__ __forceinline__ double ldg_x_ranked(const double *x, int32_t c, int32
 {
     double v;
     const uint64_t pol = c < hot_l2 ? pol_last : pol_first;
+    // (one instruction per asm: a two-instruction block is not if-converted and every gather ends up in its own branch)
     if (c < hot_l1)
-        asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %2, 8, %1;\n\tld.global.nc.L1::evict_last.L2::cache_hint.f64 %0, [a], %3;\n\t}"
-                     : "=d"(v)
-                     : "l"(x), "r"(c), "l"(pol));
+        asm volatile("ld.global.nc.L1::evict_last.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(x + c), "l"(pol));
     else
-        asm volatile("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %2, 8, %1;\n\tld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [a], %3;\n\t}"
-                     : "=d"(v)
-                     : "l"(x), "r"(c), "l"(pol));
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(x + c), "l"(pol));
     return v;
 }
 // x[c] through the read-only path; the address is formed inside the asm (one IMAD.WIDE -- left to the compiler, the
@@ -134,6 +131,12 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
 #endif
 #ifndef SMVP_SCAN_EXIT
 #define SMVP_SCAN_EXIT 0
+#endif
+#ifndef SMVP_UNIFORM_TILES
+#define SMVP_UNIFORM_TILES 1 // broadcast the warp index / tile coordinates from lane 0 so the bookkeeping lives in uniform registers
+#endif
+#ifndef SMVP_OLD_WALK
+#define SMVP_OLD_WALK 0 // A/B: the nested "live slot / row end" walk the flattened one replaced
 #endif
 #ifndef SMVP_PIN_BASES
 #define SMVP_PIN_BASES 0 // pin the lane's two shared-window bases in registers (fewer instructions, but the 14-item configurations spill)
@@ -383,7 +386,7 @@ __device__ __forceinline__ TileView make_tile(int32_t r0, int32_t r1, int32_t t,
 // never meets a block-wide barrier: warps of a CTA drift apart freely, so while one waits for HBM
 // or for its x gathers the others walk.  Rows cut by lane boundaries are stitched with a segmented
 // warp scan (__shfl_up_sync), rows cut by tile boundaries by the fix-up kernel -- fixed order, no atomics.
-template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT, bool RANKED>
+template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT, bool RANKED, bool UNI>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     csr_merge_warp_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_ind, const double *__restrict__ val,
                           const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int32_t rows,
@@ -396,10 +399,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     extern __shared__ __align__(128) unsigned char stage_mem[];
     __shared__ __align__(8) uint64_t full_bar[WARPS];
 
-    // the warp index and the tile coordinates below are broadcast from lane 0: the values are the same in every lane
+    // UNI: the warp index and the tile coordinates below are broadcast from lane 0.  The values are the same in every lane
     // anyway, but the broadcast lets the compiler PROVE it and keep the whole tile bookkeeping (and the operands of the
-    // bulk copies) in uniform registers instead of electing a lane and converting per copy
-    const int lane = threadIdx.x & 31, w = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    // bulk copies) in uniform registers instead of electing a lane and converting per copy.  Measured on B200
+    // (profiles/r01_logs/diet_bisect.log): stencil configuration 2.78 -> 2.69 ms, but the R-MAT configuration 5.67 ->
+    // 6.39 ms, so it is a per-configuration switch (last column of SMVP_WMERGE_CFGS).
+#define SMVP_BCAST(v) ((UNI && SMVP_UNIFORM_TILES) ? __shfl_sync(0xffffffffu, (v), 0) : (v))
+    const int lane = threadIdx.x & 31, w = SMVP_BCAST((int)(threadIdx.x >> 5));
     const int64_t total = (int64_t)rows + nnz;
     unsigned char *base = stage_mem + (size_t)w * Shape::SMEM_BYTES;
     uint64_t *my_bar = &full_bar[w];
@@ -436,8 +442,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     int32_t cur_r0 = 0, cur_r1 = 0; // merge coordinates of the tile in flight: the only tile state kept across the loop
     if (t < num_tiles)
     {
-        cur_r0 = __shfl_sync(0xffffffffu, __ldg(tile_row + t), 0);
-        cur_r1 = __shfl_sync(0xffffffffu, __ldg(tile_row + t + 1), 0);
+        cur_r0 = SMVP_BCAST(__ldg(tile_row + t));
+        cur_r1 = SMVP_BCAST(__ldg(tile_row + t + 1));
         if (lane == 0)
             issue(make_tile(cur_r0, cur_r1, t, Shape::TILE, total));
     }
@@ -569,6 +575,31 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             // "no further row end of mine" = never).  Dead slots (q >= cnt) hold +0.0, and a partial sum that starts at
             // +0.0 can never become -0.0, so adding them is exact: the loop needs no "is this slot live" test, and the row
             // ends that follow my last nonzero are flushed by the same test at the first dead slot.
+#if SMVP_OLD_WALK
+            int32_t row = i0;
+            int32_t end = row < rows_t ? row_end(row) : 0x7fffffff;
+#pragma unroll
+            for (int q = 0; q < IPT; q++)
+            {
+                if (q < cnt)
+                {
+                    while (end <= j0 + q)
+                    {
+                        if (!has_first)
+                        {
+                            has_first = true;
+                            first_sum = sum;
+                        }
+                        else
+                            store_y<FANOUT>(y, fan, (int64_t)tile_r0 + row, sum);
+                        sum = 0.0;
+                        row++;
+                        end = row < rows_t ? row_end(row) : 0x7fffffff;
+                    }
+                    sum = __dadd_rn(sum, prod[q]);
+                }
+            }
+#else
             int32_t row = i0;
             int32_t until = (row < i_next ? row_end(row) : 0x7fffffff) - j0;
 #pragma unroll
@@ -592,6 +623,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                 }
                 sum = __dadd_rn(sum, prod[q]);
             }
+#endif
             // every row end of mine has at most IPT - 1 of my nonzeros before it, so the loop above has seen them all;
             // this is only a safety net
             while (row < i_next)
@@ -613,8 +645,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         const int32_t tn = t + warp_stride;
         if (tn < num_tiles && tn > t)
         {
-            cur_r0 = __shfl_sync(0xffffffffu, __ldg(tile_row + tn), 0);
-            cur_r1 = __shfl_sync(0xffffffffu, __ldg(tile_row + tn + 1), 0);
+            cur_r0 = SMVP_BCAST(__ldg(tile_row + tn));
+            cur_r1 = SMVP_BCAST(__ldg(tile_row + tn + 1));
             if (lane == 0)
                 issue(make_tile(cur_r0, cur_r1, tn, Shape::TILE, total));
         }
@@ -745,14 +777,14 @@ static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
     return SMVP_OK;
 }
 
-#define SMVP_WMERGE_CFGS(X) \
-    X(0, 2, 14, 1, 16)      \
-    X(1, 2, 10, 1, 16)      \
-    X(2, 4, 14, 1, 8)       \
-    X(3, 2, 12, 1, 16)      \
-    X(4, 2, 10, 1, 14)      \
-    X(5, 2, 7, 1, 16)       \
-    X(6, 2, 9, 1, 16)
+#define SMVP_WMERGE_CFGS(X)    \
+    X(0, 2, 14, 1, 16, true)   \
+    X(1, 2, 10, 1, 16, false)  \
+    X(2, 4, 14, 1, 8, true)    \
+    X(3, 2, 12, 1, 16, true)   \
+    X(4, 2, 10, 1, 14, false)  \
+    X(5, 2, 7, 1, 16, false)   \
+    X(6, 2, 9, 1, 16, false)
 
 // how much of the rank-ordered x a relabelled multiply asks L1 / L2 to retain (entries; SMVP_HOT_L1 / SMVP_HOT_L2)
 static void hot_limits(int32_t *l1, int32_t *l2)
@@ -762,13 +794,13 @@ static void hot_limits(int32_t *l1, int32_t *l2)
     *l2 = e2 && e2[0] ? atoi(e2) : (4 << 20); // 32 MB
 }
 
-template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT, bool RANKED>
+template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT, bool RANKED, bool UNI>
 static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, const YFan *fanp, cudaStream_t s, int32_t tile_begin,
                          int32_t tile_end)
 {
     using Shape = MergeShape<32, IPT, STAGES>;
     constexpr int SMEM = WARPS * Shape::SMEM_BYTES;
-    auto kern = csr_merge_warp_kernel<WARPS, IPT, STAGES, MINB, FANOUT, RANKED>;
+    auto kern = csr_merge_warp_kernel<WARPS, IPT, STAGES, MINB, FANOUT, RANKED, UNI>;
     int32_t hot_l1 = 0, hot_l2 = 0;
     if (RANKED)
         hot_limits(&hot_l1, &hot_l2);
@@ -804,8 +836,8 @@ static int wmerge_tile_items(int cfg)
 {
     switch (cfg)
     {
-#define X(id, wp, i, st, mb) \
-    case id:                 \
+#define X(id, wp, i, st, mb, un) \
+    case id:                     \
         return 32 * i;
         SMVP_WMERGE_CFGS(X)
 #undef X
@@ -827,13 +859,13 @@ static int csr_mult_merge(smvp_csr *A, const double *d_x, double *d_y, const YFa
     const bool ranked = A->relabel_state == 1 && !(rh && rh[0] == '0');
     switch (cfg)
     {
-#define X(id, wp, i, st, mb)                                                                                       \
-    case id:                                                                                                       \
-        if (ranked)                                                                                                \
-            return fan ? launch_wmerge<wp, i, st, mb, true, true>(A, d_x, d_y, fan, s, tile_begin, tile_end)       \
-                       : launch_wmerge<wp, i, st, mb, false, true>(A, d_x, d_y, nullptr, s, tile_begin, tile_end); \
-        return fan ? launch_wmerge<wp, i, st, mb, true, false>(A, d_x, d_y, fan, s, tile_begin, tile_end)          \
-                   : launch_wmerge<wp, i, st, mb, false, false>(A, d_x, d_y, nullptr, s, tile_begin, tile_end);
+#define X(id, wp, i, st, mb, un)                                                                                       \
+    case id:                                                                                                           \
+        if (ranked)                                                                                                    \
+            return fan ? launch_wmerge<wp, i, st, mb, true, true, un>(A, d_x, d_y, fan, s, tile_begin, tile_end)       \
+                       : launch_wmerge<wp, i, st, mb, false, true, un>(A, d_x, d_y, nullptr, s, tile_begin, tile_end); \
+        return fan ? launch_wmerge<wp, i, st, mb, true, false, un>(A, d_x, d_y, fan, s, tile_begin, tile_end)          \
+                   : launch_wmerge<wp, i, st, mb, false, false, un>(A, d_x, d_y, nullptr, s, tile_begin, tile_end);
         SMVP_WMERGE_CFGS(X)
 #undef X
     default:
