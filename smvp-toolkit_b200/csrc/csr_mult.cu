@@ -784,7 +784,8 @@ static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
     X(3, 2, 12, 1, 16, true)   \
     X(4, 2, 10, 1, 14, false)  \
     X(5, 2, 7, 1, 16, false)   \
-    X(6, 2, 9, 1, 16, false)
+    X(6, 2, 9, 1, 16, false)   \
+    X(7, 4, 14, 1, 9, true)
 
 // how much of the rank-ordered x a relabelled multiply asks L1 / L2 to retain (entries; SMVP_HOT_L1 / SMVP_HOT_L2)
 static void hot_limits(int32_t *l1, int32_t *l2)
