@@ -127,7 +127,7 @@ struct smvp_csr
     int32_t pipe_cfg, pipe_ranges;
     int32_t pipe_tile[65], pipe_row[65], pipe_xneed[64];
     void *pipe_res; // streams and events of that pass, created on first use (csr_mult.cu)
-    // popularity relabelling of the column space (csr_relabel.cu): 0 undecided, 1 in use, -1 not worth it
+    // popularity relabelling of the column space (relabel.cu): 0 undecided, 1 in use, -1 not worth it
     int32_t relabel_state;
     int32_t *col_rel;    // [nnz]  rank of col_ind[j]; what the kernels read instead of col_ind when in use
     int32_t *x_order;    // [cols] column with rank p
@@ -137,9 +137,9 @@ struct smvp_csr
 namespace smvp
 {
 void csr_pipe_release(smvp_csr *A);                                // csr_mult.cu
-int csr_relabel_plan(smvp_csr *A, cudaStream_t s);                 // csr_relabel.cu
-int csr_relabel_x(smvp_csr *A, const double *d_x, cudaStream_t s); // csr_relabel.cu
-void csr_relabel_release(smvp_csr *A);                             // csr_relabel.cu
+int csr_relabel_plan(smvp_csr *A, cudaStream_t s);                 // relabel.cu
+int csr_relabel_x(smvp_csr *A, const double *d_x, cudaStream_t s); // relabel.cu
+void csr_relabel_release(smvp_csr *A);                             // relabel.cu
 } // namespace smvp
 
 struct smvp_tjds
@@ -165,7 +165,7 @@ struct smvp_tjds
     long long *acc;          // [2*rows] hi/lo integer accumulators
     int32_t *x_exp;          // [1] exponent bound of max |x|
     double *d_x, *d_y;
-    // popularity relabelling of the ROW space (csr_relabel.cu): 0 undecided, 1 in use, -1 not worth it
+    // popularity relabelling of the ROW space (relabel.cu): 0 undecided, 1 in use, -1 not worth it
     int32_t relabel_state;
     int32_t *row_rel;        // [nnz]  rank of row_ind[j]; what the kernels scatter through when in use
     int32_t *row_rank;       // [rows] rank of row r
@@ -173,6 +173,6 @@ struct smvp_tjds
 };
 namespace smvp
 {
-int tjds_relabel_plan(smvp_tjds *A, cudaStream_t s); // csr_relabel.cu
-void tjds_relabel_release(smvp_tjds *A);             // csr_relabel.cu
+int tjds_relabel_plan(smvp_tjds *A, cudaStream_t s); // relabel.cu
+void tjds_relabel_release(smvp_tjds *A);             // relabel.cu
 } // namespace smvp

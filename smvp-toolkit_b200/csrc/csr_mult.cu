@@ -83,7 +83,7 @@ __device__ __forceinline__ double ldg_x(const double *p, uint64_t pol)
     return __ldg(p);
 #endif
 }
-// x gather of a popularity-relabelled matrix (csr_relabel.cu): the column index IS the popularity rank, so the
+// x gather of a popularity-relabelled matrix (relabel.cu): the column index IS the popularity rank, so the
 // load can say how long the line deserves to live.  rank < hot_l1: keep in L1; rank < hot_l2: keep in L2
 // (evict-last) while the matrix streams and the cold gathers pass through evict-first and do not allocate in L1.
 __device__ __forceinline__ double ldg_x_ranked(const double *x, int32_t c, int32_t hot_l1, int32_t hot_l2, uint64_t pol_last,
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) csr_vector_kernel(const int32_t *__restri
         store_y<FANOUT>(y, fan, row, sum);
 }
 
-// the column indices the multiply kernels read: the relabelled copy when that plan is in use (csr_relabel.cu)
+// the column indices the multiply kernels read: the relabelled copy when that plan is in use (relabel.cu)
 static inline const int32_t *mult_cols(const smvp_csr *A) { return A->relabel_state == 1 ? A->col_rel : A->col_ind; }
 
 template <int LPR>
@@ -893,6 +893,8 @@ using namespace smvp;
 // x is already in the space the kernels index (x itself, or x_rel when the relabelling plan is in use)
 static int csr_mult_launch(smvp_csr *A, const double *x, double *d_y, const YFan *fan, int variant, cudaStream_t s)
 {
+    if (A->rows == 0)
+        return SMVP_OK;
     const int v = csr_resolve_variant(A, variant);
     int rc = (v == SMVP_CSR_VECTOR) ? csr_mult_vector(A, x, d_y, fan, s) : csr_mult_merge(A, x, d_y, fan, s);
     if (rc != SMVP_OK)

@@ -1,12 +1,13 @@
-// csr_relabel.cu -- popularity relabelling of the CSR column space (a multiply-side plan; the CSR arrays the
-// reference defines, main-cli.c:61-66, stay untouched and bit-exact).
+// relabel.cu -- popularity relabelling of an index space: the COLUMNS of a CSR handle (the gather side) and the ROWS
+// of a TJDS handle (the scatter side).  A multiply-side plan: the arrays the reference defines (CSRData / TJDSData,
+// main-cli.c:61-75) stay untouched and bit-exact.
 //
 // Why: the CSR loop (main-cli.c:410-416) gathers x[col_ind[j]].  On a power-law matrix whose x does not fit
 // the 126 MB L2 (R-MAT scale 26: 537 MB) half of those 8-byte gathers miss L2 and each miss moves a 32-byte
 // DRAM sector: ncu counted 30.6 GB of DRAM traffic for 14.1 GB of algorithmic bytes
 // (profiles/r01_csr_merge_warp_rmat26.txt).  The gathers are far from uniform, though: a few million columns
 // receive most of them -- but they are scattered over the whole index range, so they share their sectors and
-// cache lines with cold columns.
+// cache lines with cold columns.  The TJDS loop (main-cli.c:1013-1020) has the mirror problem on y[row_ind[j]].
 //
 // What: number the columns by descending entry count (ties keep column order) -- exactly the permutation
 // the TJDS format defines (main-cli.c:868, txtable_comparator_len :209-223) -- and keep
@@ -14,11 +15,13 @@
 //     x_order[p] = column with rank p      x_rel[p] = x[x_order[p]] is formed once per x
 // The hot columns become one dense prefix of x_rel that stays resident in L2 (and partly in L1).  Entries keep
 // their order inside each row, so every row is summed in exactly the order it was before: y is bit-identical
-// with and without the plan.
+// with and without the plan.  For TJDS: row_rel[j] = rank[row_ind[j]], sums land in rank order, one pass per
+// multiply puts them back (y[r] = y_rel[row_rank[r]]).
 //
-// When (AUTO): x larger than RELABEL_MIN_COLS entries, and the RELABEL_HOT_COLS most popular columns hold at
-// least half of the nonzeros and at least four times their fair share.  Banded and uniform matrices fail the
-// test and keep their natural (already local, or hopeless) order.  SMVP_CSR_RELABEL=1 / 0 forces it on / off.
+// When (AUTO): the index space has at least RELABEL_MIN_COLS entries, and the RELABEL_HOT_COLS most popular ones
+// hold at least half of the nonzeros and at least four times their fair share.  Banded and uniform matrices fail
+// the test and keep their natural (already local, or hopeless) order.  SMVP_CSR_RELABEL / SMVP_TJDS_RELABEL = 1 / 0
+// force it on / off.
 #include "common.cuh"
 
 namespace smvp

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(256) tjds_unrank_y_kernel(const double *__rest
         y[r] = __ldg(y_rel + __ldg(row_rank + r));
 }
 
-// the row indices the kernels scatter through: the relabelled copy when that plan is in use (csr_relabel.cu)
+// the row indices the kernels scatter through: the relabelled copy when that plan is in use (relabel.cu)
 static inline const int32_t *mult_rows(const smvp_tjds *A) { return A->relabel_state == 1 ? A->row_rel : A->row_ind; }
 
 static int tjds_plan(smvp_tjds *A, cudaStream_t s)

@@ -372,7 +372,7 @@ def _powerlaw_coo(rng, m, n, nnz, power):
 
 
 def test_csr_relabel_forced_bit_identical(eng, monkeypatch):
-    """The popularity relabelling of the column space (csr_relabel.cu) is a multiply-side plan: the exported CSR
+    """The popularity relabelling of the column space (relabel.cu) is a multiply-side plan: the exported CSR
     arrays stay bit-exact against the oracle, and because entries keep their order inside each row, y is
     bit-identical with and without it -- for both kernels, through every entry point."""
     import torch

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""A/B of the popularity relabelling (csr_relabel.cu) on an R-MAT matrix (GPU box):
+"""A/B of the popularity relabelling (relabel.cu) on an R-MAT matrix (GPU box):
     python tools/sweep_rmat.py --scale 26 --cfgs 4,1,6,5 [--steps 10]
 Builds the same CSR twice (SMVP_CSR_RELABEL=0 / 1), times the merge-path configurations and the vector kernel on
 both with x declared once (smvp_csr_set_x_device), times the x permutation itself, and checks that the relabelled
