@@ -28,10 +28,10 @@ $(LIB)/libsmvp_cuda.so: $(CU_OBJS)
 
 $(LIB)/libsmvp_host.so: $(HOST_LIB) $(PKG)/host/smvp_mmio.h $(PKG)/host/smvp_host.h
 	@mkdir -p $(LIB)
-	$(CC) $(CFLAGS) -fPIC -shared -o $@ $(HOST_LIB) -lm
+	$(CC) $(CFLAGS) -fPIC -shared -o $@ $(HOST_LIB) -lm -lpthread
 
 $(LIB)/smvp-toolkit-cli: $(PKG)/host/main-cli.c $(HOST_LIB) $(LIB)/libsmvp_cuda.so
-	$(CC) $(CFLAGS) -o $@ $(PKG)/host/main-cli.c $(HOST_LIB) -L$(LIB) -lsmvp_cuda -Wl,-rpath,'$$ORIGIN' -lm
+	$(CC) $(CFLAGS) -o $@ $(PKG)/host/main-cli.c $(HOST_LIB) -L$(LIB) -lsmvp_cuda -Wl,-rpath,'$$ORIGIN' -lm -lpthread
 
 oracle:
 	$(MAKE) -C oracle all

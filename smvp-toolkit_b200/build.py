@@ -94,10 +94,10 @@ def build_host(force=False):
     common = ["gcc", "-O2", "-std=gnu11", "-Wall", "-Wextra", "-D_XOPEN_SOURCE=700", "-I" + os.path.join(REPO, "include"),
               "-I" + HOST]
     if force or _newer(HOST_SO, lib_srcs + hdrs):
-        _run(common + ["-fPIC", "-shared", "-o", HOST_SO] + lib_srcs + ["-lm"])
+        _run(common + ["-fPIC", "-shared", "-o", HOST_SO] + lib_srcs + ["-lm", "-lpthread"])
     main = os.path.join(HOST, "main-cli.c")
     if os.path.exists(main) and (force or _newer(CLI, csrcs + hdrs + [CUDA_SO])):
-        _run(common + ["-o", CLI] + csrcs + ["-L" + LIB, "-lsmvp_cuda", "-Wl,-rpath,$ORIGIN", "-lm"])
+        _run(common + ["-o", CLI] + csrcs + ["-L" + LIB, "-lsmvp_cuda", "-Wl,-rpath,$ORIGIN", "-lm", "-lpthread"])
     return HOST_SO
 
 

@@ -198,3 +198,87 @@ def test_cli_usage_and_option_errors():
     assert r.returncode == 1 and "Required parameters not present on first line of file." in r.stdout
     r = subprocess.run([cli, "-c", "a.mtx", "b.mtx"], capture_output=True, text=True)
     assert r.returncode == 1 and "Must specify a single input file" in r.stderr
+
+
+# ------------------------------------------------------------------ chunked / threaded entry parser
+def _with_threads(monkeypatch, threads, min_chunk=64):
+    monkeypatch.setenv("SMVP_LOAD_THREADS", str(threads))
+    monkeypatch.setenv("SMVP_LOAD_MIN_CHUNK", str(min_chunk))
+
+
+def _write_mtx(path, field, m, n, lines, declared=None):
+    with open(path, "w") as f:
+        f.write("%%%%MatrixMarket matrix coordinate %s general\n%% a comment\n%d %d %d\n" % (field, m, n,
+                                                                                          len(lines) if declared is None else declared))
+        f.write("".join(lines))
+
+
+def test_threaded_loader_is_bit_identical_to_the_sequential_one(host, tmp_path, monkeypatch):
+    """The chunked parser (one line-aligned chunk per thread, exact fast path for short decimals, strtod for the rest)
+    must return exactly the entries of the sequential token parser: every value format strtod accepts, every thread
+    count, chunk borders anywhere."""
+    rng = np.random.default_rng(5)
+    m, n, nnz = 5000, 7000, 20000
+    fmts = ["%.17g", "%.6f", "%.3e", "%d", "%.15g", "%.16e", "%g"]
+    vals = rng.uniform(-1e3, 1e3, nnz) * 10.0 ** rng.integers(-30, 30, nnz)
+    special = ["0", "-0.0", "1e-400", "1e400", "-inf", "nan", "0x1.8p3", ".5", "5.", "+7", "1E5", "00012.50", "4.9e-324",
+               "123456789012345678901234567890", "0.000000000000000000001234567890123456789"]
+    lines = []
+    for i in range(nnz):
+        tok = special[i % len(special)] if i % 97 == 0 else fmts[i % len(fmts)] % (int(vals[i]) % 10 ** 9 if fmts[i % len(fmts)] == "%d" else vals[i])
+        sep = ["\n", "\r\n", "  \n", "\t\n"][i % 4]
+        lines.append("%d %s%d %s%s" % (rng.integers(1, m + 1), " " * (i % 3), rng.integers(1, n + 1), tok, sep))
+    path = str(tmp_path / "mixed.mtx")
+    _write_mtx(path, "real", m, n, lines)
+    _with_threads(monkeypatch, 1)
+    rc, ref = load(host, path)
+    assert rc == 0 and len(ref[2]) == nnz
+    # the sequential parser is strtol/strtod: Python's float() agrees on every decimal token
+    for i in (0, 1, 2, 3, 5, 6, 8, 9, 10):
+        tok = lines[i].split()[2]
+        assert ref[2]["val"][i] == float(tok)
+    for threads in (2, 3, 8, 64):
+        _with_threads(monkeypatch, threads)
+        rc, got = load(host, path)
+        assert rc == 0
+        assert got[2].tobytes() == ref[2].tobytes(), "threads=%d" % threads
+    # pattern files: two tokens per entry
+    plines = ["%d %d\n" % (rng.integers(1, m + 1), rng.integers(1, n + 1)) for _ in range(5000)]
+    ppath = str(tmp_path / "pattern.mtx")
+    _write_mtx(ppath, "pattern", m, n, plines)
+    _with_threads(monkeypatch, 1)
+    rc, pref = load(host, ppath)
+    _with_threads(monkeypatch, 5)
+    rc2, pgot = load(host, ppath)
+    assert rc == 0 and rc2 == 0 and pgot[2].tobytes() == pref[2].tobytes() and np.all(pref[2]["val"] == 1.0)
+
+
+def test_threaded_loader_keeps_the_token_semantics(host, tmp_path, monkeypatch):
+    """fscanf semantics (main-cli.c:1427-1441) survive the chunking: entries may be split over lines (the chunked path
+    steps aside), exactly nnz entries are read and what follows is ignored, too few or malformed entries are the
+    same error with any thread count."""
+    m = n = 50
+    entries = [(i % m + 1, (7 * i) % n + 1, 0.5 * i) for i in range(400)]
+    free_form = "".join("%d\n%d\n%r\n" % e if k % 2 else "%d %d %r " % e for k, e in enumerate(entries)) + "\n"
+    cases = {
+        "freeform": (free_form, 400, 0),
+        "trailing": ("".join("%d %d %r\n" % e for e in entries) + "9 9 9.0\nthis is ignored\n", 400, 0),
+        "too_few": ("".join("%d %d %r\n" % e for e in entries[:399]), 400, 104),
+        "bad_token": ("".join("%d %d %r\n" % e for e in entries[:200]) + "3 x 1.0\n" + "".join("%d %d %r\n" % e for e in entries[200:]), 400, 104),
+        "fortran_d": ("".join("%d %d %r\n" % e for e in entries[:399]) + "1 1 1.5d3\n", 400, 0),
+    }
+    for name, (body, declared, want_rc) in cases.items():
+        path = str(tmp_path / (name + ".mtx"))
+        with open(path, "w") as f:
+            f.write("%%%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (m, n, declared))
+            f.write(body)
+        results = []
+        for threads in (1, 4, 16):
+            _with_threads(monkeypatch, threads, min_chunk=16)
+            rc, got = load(host, path)
+            results.append((rc, None if got is None else got[2].tobytes()))
+        assert results[0][0] == want_rc, (name, results[0][0])
+        assert results[1] == results[0] and results[2] == results[0], name
+        if want_rc == 0 and name != "fortran_d":
+            _, got = load(host, path)
+            assert [(int(r) + 1, int(c) + 1, float(v)) for r, c, v in got[2]] == entries
