@@ -508,6 +508,76 @@ int smvp_load_mtx_ex(const char *path, int expand_symmetric, MM_typecode *matcod
     return 0;
 }
 
+/* The vector part of a report, "%g" per row (main-cli.c:309-314), for vectors of millions of rows: every thread
+ * formats a contiguous block of rows with the same snprintf("%g") into its own buffer, the buffers are written in
+ * order.  Same bytes as the fprintf loop; -1 = could not (memory / threads), the caller then runs that loop. */
+#define REPORT_PARALLEL_ROWS (1 << 18)
+
+typedef struct
+{
+    const double *y;
+    int begin, end, rows;
+    char *buf;
+    size_t len;
+} fmt_block;
+
+static void *fmt_block_fn(void *arg)
+{
+    fmt_block *b = (fmt_block *)arg;
+    size_t cap = (size_t)(b->end - b->begin) * 26 + 8, n = 0; /* "%g" of a double is at most 13 characters */
+    int i;
+    b->buf = (char *)malloc(cap);
+    b->len = 0;
+    if (!b->buf)
+        return NULL;
+    for (i = b->begin; i < b->end; i++)
+    {
+        n += (size_t)snprintf(b->buf + n, cap - n, "%g", b->y[i]);
+        n += (size_t)snprintf(b->buf + n, cap - n, i < b->rows - 1 ? "\n" : "\n]\n\n");
+    }
+    b->len = n;
+    return NULL;
+}
+
+static int write_vector_parallel(FILE *f, const double *y, int rows)
+{
+    fmt_block blk[256];
+    int n = load_threads((size_t)rows * 64), k, rc = 0;
+    if (n < 2)
+        return -1;
+    for (k = 0; k < n; k++)
+    {
+        blk[k].y = y;
+        blk[k].rows = rows;
+        blk[k].begin = (int)((int64_t)rows * k / n);
+        blk[k].end = (int)((int64_t)rows * (k + 1) / n);
+        blk[k].buf = NULL;
+    }
+    {
+        pthread_t tid[256];
+        int started[256];
+        for (k = 1; k < n; k++)
+            started[k] = pthread_create(&tid[k], NULL, fmt_block_fn, &blk[k]) == 0;
+        fmt_block_fn(&blk[0]);
+        for (k = 1; k < n; k++)
+        {
+            if (started[k])
+                pthread_join(tid[k], NULL);
+            else
+                fmt_block_fn(&blk[k]);
+        }
+    }
+    for (k = 0; k < n; k++)
+        if (!blk[k].buf)
+            rc = -1;
+    for (k = 0; k < n && rc == 0; k++)
+        if (fwrite(blk[k].buf, 1, blk[k].len, f) != blk[k].len)
+            rc = -2; /* partial output: do not let the caller append the vector a second time */
+    for (k = 0; k < n; k++)
+        free(blk[k].buf);
+    return rc == -2 ? 0 : rc;
+}
+
 int smvp_write_report(const char *input_file_name, const char *report_dir, const char *alg_name, int nnz, int rows,
                       int iters, const double *y, const smvp_time_stats_t *t, unsigned long unix_time, char *out_path,
                       size_t out_path_len)
@@ -554,6 +624,11 @@ int smvp_write_report(const char *input_file_name, const char *report_dir, const
     fprintf(f, "Time StDev: %g ms\n\n", t->time_stdev);
     fprintf(f, "Output vector (one cell per line):\n");
     fprintf(f, "[\n");
+    if (rows >= REPORT_PARALLEL_ROWS && write_vector_parallel(f, y, rows) == 0)
+    {
+        fclose(f);
+        return 0;
+    }
     for (i = 0; i < rows; i++)
     {
         fprintf(f, "%g", y[i]);

@@ -282,3 +282,40 @@ def test_threaded_loader_keeps_the_token_semantics(host, tmp_path, monkeypatch):
         if want_rc == 0 and name != "fortran_d":
             _, got = load(host, path)
             assert [(int(r) + 1, int(c) + 1, float(v)) for r, c, v in got[2]] == entries
+
+
+def test_report_writer_threaded_vector_is_byte_identical(host, tmp_path, monkeypatch):
+    """Vectors of 2^18 rows and more are formatted by several threads (same snprintf("%g") per row, blocks written in
+    order): the file must equal, byte for byte, the one the plain fprintf loop writes -- and Python's own %g."""
+    import time
+
+    rng = np.random.default_rng(9)
+    rows = (1 << 18) + 12345
+    y = rng.uniform(-1, 1, rows) * 10.0 ** rng.integers(-12, 12, rows)
+    y[::1000] = 0.0
+    y[1::1000] = -0.0
+    y[2::5000] = np.inf
+    y[3::5000] = np.nan
+    y[4::5000] = 1e-310  # subnormal
+    y[5::5000] = np.round(y[5::5000])
+    y = np.ascontiguousarray(y)
+    st = TimeStats(1.5, 0.5, 0.1, 0.4, 0.6)
+    texts, secs = [], []
+    for threads in (1, 7):
+        monkeypatch.setenv("SMVP_LOAD_THREADS", str(threads))
+        d = tmp_path / ("t%d" % threads)
+        d.mkdir()
+        out = ctypes.create_string_buffer(4096)
+        t0 = time.time()
+        rc = host.smvp_write_report(b"big.mtx", str(d).encode(), b"CSR", 123, rows, 3, y.ctypes.data_as(ctypes.c_void_p),
+                                    ctypes.byref(st), 1700000000, out, 4096)
+        secs.append(time.time() - t0)
+        assert rc == 0
+        texts.append(open(out.value.decode()).read())
+    assert texts[0] == texts[1]
+    body = texts[1].split("[\n", 1)[1]
+    assert body.endswith("\n]\n\n")
+    got = body[: -len("\n]\n\n")].split("\n")
+    assert len(got) == rows
+    for i in list(range(0, 3000)) + list(range(rows - 50, rows)):
+        assert got[i] == ("%g" % y[i]), i
