@@ -81,6 +81,21 @@ def csr_mult(row_ptr, col_ind, val, x):
     return y
 
 
+def csr_mult_timed_mt(row_ptr, col_ind, val, x, iters, nthreads):
+    """The reference's CSR loop over nnz-balanced row blocks on `nthreads` host threads (not what the reference does:
+    it is single-threaded).  y is bit-identical to csr_mult."""
+    rows = len(row_ptr) - 1
+    x = np.ascontiguousarray(x, np.float64)
+    y = np.zeros(rows, np.float64)
+    ms = np.zeros(iters, np.float64)
+    f = lib().oracle_csr_mult_timed_mt
+    f.argtypes = [ctypes.c_int32] + [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    f.restype = ctypes.c_int
+    if f(rows, _p(row_ptr), _p(col_ind), _p(val), _p(x), _p(y), iters, _p(ms), nthreads) != 0:
+        raise RuntimeError("oracle_csr_mult_timed_mt could not start its threads")
+    return y, ms
+
+
 def csr_mult_timed(row_ptr, col_ind, val, x, iters):
     rows = len(row_ptr) - 1
     x = np.ascontiguousarray(x, np.float64)

@@ -23,6 +23,7 @@
  * Build: gcc -O3 -ffp-contract=off -fPIC -shared  (no FMA contraction: the reference
  * binary is plain x86-64 -O3, mulsd+addsd; main-cli.c:414, build/build.ninja:111).
  */
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -177,6 +178,117 @@ void oracle_csr_mult_timed(int32_t rows, const int32_t *row_ptr, const int32_t *
         clock_gettime(CLOCK_MONOTONIC_RAW, &t1);
         ms_each[it] = ((t1.tv_sec * 1e9 + t1.tv_nsec) - (t0.tv_sec * 1e9 + t0.tv_nsec)) / 1e6;
     }
+}
+
+/*
+ * The same loop, rows cut into nnz-balanced blocks over `nthreads` host threads -- NOT something the reference
+ * does (it is single-threaded); bench.py reports it next to the 1-thread number as "what every core of the box
+ * could do with the reference's loop".  Each row is still summed left to right by one thread, so y is
+ * bit-identical to oracle_csr_mult.  ms_each = wall time of each pass, first thread in to last thread out.
+ */
+typedef struct
+{
+    int32_t r0, r1;
+    const int32_t *row_ptr, *col_ind;
+    const double *val, *x;
+    double *y;
+    int iters;
+    pthread_barrier_t *bar;
+} csr_mt_arg;
+
+static void *csr_mt_fn(void *argp)
+{
+    csr_mt_arg *a = (csr_mt_arg *)argp;
+    int it;
+    int32_t r, j;
+    for (it = 0; it < a->iters; it++)
+    {
+        for (r = a->r0; r < a->r1; r++)
+            a->y[r] = 0.0;
+        pthread_barrier_wait(a->bar); /* pass starts */
+        for (r = a->r0; r < a->r1; r++)
+            for (j = a->row_ptr[r]; j < a->row_ptr[r + 1]; j++)
+                a->y[r] += a->val[j] * a->x[a->col_ind[j]];
+        pthread_barrier_wait(a->bar); /* pass ends */
+    }
+    return NULL;
+}
+
+int oracle_csr_mult_timed_mt(int32_t rows, const int32_t *row_ptr, const int32_t *col_ind, const double *val,
+                             const double *x, double *y, int iters, double *ms_each, int nthreads)
+{
+    pthread_t *tid;
+    csr_mt_arg *args;
+    pthread_barrier_t bar;
+    struct timespec t0, t1;
+    int k, it, started = 0;
+    const int64_t nnz = rows > 0 ? row_ptr[rows] : 0;
+    if (nthreads < 1)
+        nthreads = 1;
+    tid = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
+    args = (csr_mt_arg *)malloc(sizeof(csr_mt_arg) * (size_t)nthreads);
+    if (!tid || !args || pthread_barrier_init(&bar, NULL, (unsigned)nthreads + 1) != 0)
+    {
+        free(tid);
+        free(args);
+        return -1;
+    }
+    for (k = 0; k < nthreads; k++)
+    {
+        /* first row whose prefix reaches k/nthreads of the nonzeros (the engine's row-block rule) */
+        int32_t lo = 0, hi = rows;
+        const int64_t target = nnz * k / nthreads;
+        while (lo < hi)
+        {
+            const int32_t mid = lo + (hi - lo) / 2;
+            if (row_ptr[mid] < target)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        args[k].r0 = k == 0 ? 0 : lo;
+        if (k > 0)
+            args[k - 1].r1 = args[k].r0;
+        args[k].row_ptr = row_ptr;
+        args[k].col_ind = col_ind;
+        args[k].val = val;
+        args[k].x = x;
+        args[k].y = y;
+        args[k].iters = iters;
+        args[k].bar = &bar;
+    }
+    args[nthreads - 1].r1 = rows;
+    for (k = 0; k < nthreads; k++)
+    {
+        if (pthread_create(&tid[k], NULL, csr_mt_fn, &args[k]) != 0)
+            break;
+        started++;
+    }
+    if (started != nthreads) /* cannot run short-handed: the barrier counts every thread */
+    {
+        for (k = 0; k < started; k++)
+            pthread_cancel(tid[k]);
+        for (k = 0; k < started; k++)
+            pthread_join(tid[k], NULL);
+        pthread_barrier_destroy(&bar);
+        free(tid);
+        free(args);
+        return -1;
+    }
+    for (it = 0; it < iters; it++)
+    {
+        pthread_barrier_wait(&bar);
+        clock_gettime(CLOCK_MONOTONIC_RAW, &t0);
+        pthread_barrier_wait(&bar);
+        clock_gettime(CLOCK_MONOTONIC_RAW, &t1);
+        ms_each[it] = ((t1.tv_sec * 1e9 + t1.tv_nsec) - (t0.tv_sec * 1e9 + t0.tv_nsec)) / 1e6;
+    }
+    for (k = 0; k < nthreads; k++)
+        pthread_join(tid[k], NULL);
+    pthread_barrier_destroy(&bar);
+    free(tid);
+    free(args);
+    return 0;
 }
 
 /*

@@ -78,3 +78,20 @@ def test_tjds_layout_invariants_and_product(case):
         y_lim = oracle.tjds_mult(tp, np.ones(n), diag_limit=1)
         y_all = oracle.tjds_mult(tp, np.ones(n))
         assert np.all(y_lim <= y_all + 1e-12)
+
+
+def test_threaded_oracle_loop_is_bit_identical():
+    """bench.py's all-cores CPU figure runs the reference loop over nnz-balanced row blocks on several threads; every row
+    is still summed left to right by one thread, so the result equals the scalar loop bit for bit -- also with empty
+    rows, one giant row, and more threads than rows."""
+    rng = np.random.default_rng(21)
+    for m, n, nnz, threads in ((5000, 4000, 60000, 7), (3, 50000, 40000, 16), (2000, 10, 5000, 3), (1, 1, 1, 4)):
+        rows = rng.integers(0, m, nnz)
+        cols = rng.integers(0, n, nnz)
+        key = np.unique(rows.astype(np.int64) * n + cols)
+        coo = oracle.make_coo(key // n, key % n, rng.uniform(-1, 1, len(key)))
+        rp, ci, va = oracle.csr_build(coo, m, n)
+        x = rng.uniform(-1, 1, n)
+        y = oracle.csr_mult(rp, ci, va, x)
+        y_mt, ms = oracle.csr_mult_timed_mt(rp, ci, va, x, 3, threads)
+        assert np.array_equal(y.view(np.int64), y_mt.view(np.int64)) and len(ms) == 3 and np.all(ms >= 0)
