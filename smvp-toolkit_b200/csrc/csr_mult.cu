@@ -135,12 +135,6 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
 #ifndef SMVP_UNIFORM_TILES
 #define SMVP_UNIFORM_TILES 1 // broadcast the warp index / tile coordinates from lane 0 so the bookkeeping lives in uniform registers
 #endif
-#ifndef SMVP_OLD_WALK
-#define SMVP_OLD_WALK 0 // A/B: the nested "live slot / row end" walk the flattened one replaced
-#endif
-#ifndef SMVP_PIN_BASES
-#define SMVP_PIN_BASES 0 // pin the lane's two shared-window bases in registers (fewer instructions, but the 14-item configurations spill)
-#endif
 #ifndef SMVP_X_EVICT_LAST
 #define SMVP_X_EVICT_LAST 0 // gather x with an L2 evict-last policy: measured 1 % on the stencil, 0 % on R-MAT -> off
 #endif
@@ -541,15 +535,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 
         // ---- all my gathers first, in three phases pinned by volatile asm: the column indices, then every x gather of
         // the lane (IPT independent loads in flight together -- left alone, the compiler reuses one register pair and
-        // waits for each load before issuing the next), then the products.  The two shared-window bases of the lane
-        // are pinned in registers by an opaque move, so every shared load addresses [base + constant].
+        // waits for each load before issuing the next), then the products.  (Pinning the lane's two shared-window bases
+        // in registers with an opaque move saves an address instruction per load but makes the 14-item configurations
+        // spill; the nested "live slot / row end" walk this one replaced is in profiles/r01_logs/diet_bisect.log.)
         double prod[IPT];
         {
             int32_t cq[IPT];
             uint32_t cbase = scol + 4u * (uint32_t)j0, vbase = sval + 8u * (uint32_t)j0;
-#if SMVP_PIN_BASES
-            asm volatile("" : "+r"(cbase), "+r"(vbase));
-#endif
             // (every slot gets a defined value: leaving the dead ones undefined makes the compiler carry the previous
             // tile's registers through the loop and spill them)
 #pragma unroll
@@ -575,31 +567,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             // "no further row end of mine" = never).  Dead slots (q >= cnt) hold +0.0, and a partial sum that starts at
             // +0.0 can never become -0.0, so adding them is exact: the loop needs no "is this slot live" test, and the row
             // ends that follow my last nonzero are flushed by the same test at the first dead slot.
-#if SMVP_OLD_WALK
-            int32_t row = i0;
-            int32_t end = row < rows_t ? row_end(row) : 0x7fffffff;
-#pragma unroll
-            for (int q = 0; q < IPT; q++)
-            {
-                if (q < cnt)
-                {
-                    while (end <= j0 + q)
-                    {
-                        if (!has_first)
-                        {
-                            has_first = true;
-                            first_sum = sum;
-                        }
-                        else
-                            store_y<FANOUT>(y, fan, (int64_t)tile_r0 + row, sum);
-                        sum = 0.0;
-                        row++;
-                        end = row < rows_t ? row_end(row) : 0x7fffffff;
-                    }
-                    sum = __dadd_rn(sum, prod[q]);
-                }
-            }
-#else
             int32_t row = i0;
             int32_t until = (row < i_next ? row_end(row) : 0x7fffffff) - j0;
 #pragma unroll
@@ -623,7 +590,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                 }
                 sum = __dadd_rn(sum, prod[q]);
             }
-#endif
             // every row end of mine has at most IPT - 1 of my nonzeros before it, so the loop above has seen them all;
             // this is only a safety net
             while (row < i_next)
