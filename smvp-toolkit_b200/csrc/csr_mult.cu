@@ -955,17 +955,28 @@ static int env_int(const char *name, int dflt, int lo, int hi)
 static int pipe_ranges() { return env_int("SMVP_PIPE_RANGES", 32, 1, PIPE_MAX_RANGES); }
 static int pipe_xchunks() { return env_int("SMVP_PIPE_XCHUNKS", 64, 1, PIPE_MAX_XCHUNKS); }
 
-__global__ void __launch_bounds__(256) col_max_kernel(const int32_t *__restrict__ col_ind, int64_t n0, int64_t n1,
-                                                      int32_t *__restrict__ out)
+// largest and smallest column index among nonzeros [n0, n1): out[0] = max (start -1), out[1] = min (start INT32_MAX)
+__global__ void __launch_bounds__(256) col_range_kernel(const int32_t *__restrict__ col_ind, int64_t n0, int64_t n1,
+                                                        int32_t *__restrict__ out)
 {
-    int32_t m = -1;
+    int32_t hi = -1, lo = 0x7fffffff;
     for (int64_t j = n0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n1; j += (int64_t)gridDim.x * blockDim.x)
-        m = max(m, __ldg(col_ind + j));
+    {
+        const int32_t c = __ldg(col_ind + j);
+        hi = max(hi, c);
+        lo = min(lo, c);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
-        m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m >= 0)
-        atomicMax(out, m);
+    {
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    }
+    if ((threadIdx.x & 31) == 0 && hi >= 0)
+    {
+        atomicMax(out, hi);
+        atomicMin(out + 1, lo);
+    }
 }
 
 static int pipe_plan(smvp_csr *A)
@@ -976,9 +987,15 @@ static int pipe_plan(smvp_csr *A)
         return SMVP_OK;
     const int32_t T = A->merge_tiles;
     const int64_t tile_items = A->merge_cfg;
-    int32_t *d_max = nullptr;
-    SMVP_CUDA(dev_alloc(&d_max, PIPE_MAX_RANGES));
-    cudaError_t e = cudaMemset(d_max, 0xff, sizeof(int32_t) * PIPE_MAX_RANGES); // -1: the range reads no x at all
+    int32_t *d_max = nullptr; // per range: {largest, smallest} column index
+    int32_t h_max[2 * PIPE_MAX_RANGES];
+    for (int c = 0; c < PIPE_MAX_RANGES; c++)
+    {
+        h_max[2 * c] = -1; // the range reads no x at all
+        h_max[2 * c + 1] = 0x7fffffff;
+    }
+    SMVP_CUDA(dev_alloc(&d_max, 2 * PIPE_MAX_RANGES));
+    cudaError_t e = cudaMemcpy(d_max, h_max, sizeof(h_max), cudaMemcpyHostToDevice);
     for (int c = 0; c <= NR && e == cudaSuccess; c++)
     {
         A->pipe_tile[c] = (int32_t)((int64_t)T * c / NR);
@@ -996,22 +1013,25 @@ static int pipe_plan(smvp_csr *A)
         {
             int64_t grid = ceil_div64(n1 - n0, 256 * 16);
             const int64_t cap = (int64_t)device_props().sms * 8;
-            SMVP_LAUNCH(col_max_kernel, (unsigned)(grid < cap ? grid : cap), 256, 0, 0, (const int32_t *)A->col_ind, n0, n1,
-                        d_max + c);
+            SMVP_LAUNCH(col_range_kernel, (unsigned)(grid < cap ? grid : cap), 256, 0, 0, (const int32_t *)A->col_ind, n0, n1,
+                        d_max + 2 * c);
         }
     }
-    int32_t h_max[PIPE_MAX_RANGES];
     if (e == cudaSuccess)
         e = cudaMemcpy(h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost);
     cudaFree(d_max);
     if (e != cudaSuccess)
         return cuda_fail(e, "pipe_plan", __FILE__, __LINE__);
-    int32_t need = 0; // x arrives front to back, so a range needs everything up to the largest column seen so far
+    int32_t need = 0, lowest = 0x7fffffff; // x arrives front to back: a range needs everything up to the largest column so far
     for (int c = 0; c < NR; c++)
     {
-        need = h_max[c] + 1 > need ? h_max[c] + 1 : need;
+        need = h_max[2 * c] + 1 > need ? h_max[2 * c] + 1 : need;
+        lowest = h_max[2 * c + 1] < lowest ? h_max[2 * c + 1] : lowest;
         A->pipe_xneed[c] = need;
     }
+    // nothing below the smallest column index is ever read: the upload starts there (a row block of a banded matrix,
+    // the shard of one GPU, reads a window of x, not a prefix).  Rounded down to 512 bytes.
+    A->pipe_xlo = need > 0 ? (lowest / 64) * 64 : 0;
     A->pipe_cfg = A->merge_cfg;
     A->pipe_ranges = NR;
     return SMVP_OK;
@@ -1101,12 +1121,15 @@ static int csr_mult_pipelined(smvp_csr *A, const double *x_host, double *y_host,
     }
     PipeResources &R = *static_cast<PipeResources *>(A->pipe_res);
     const int NR = A->pipe_ranges, NX = pipe_xchunks(), NS = pipe_streams();
-    const int64_t xchunk = ((ceil_div64(A->cols, NX) + 63) / 64) * 64; // entries per upload piece (512 B multiple)
+    // the part of x this matrix reads: [xlo, xhi).  Entries outside it are never gathered, so they are not uploaded
+    const int64_t xlo = A->pipe_xlo, xhi = NR > 0 ? A->pipe_xneed[NR - 1] : 0;
+    const int64_t xlen = xhi > xlo ? xhi - xlo : 0;
+    const int64_t xchunk = ((ceil_div64(xlen > 0 ? xlen : 1, NX) + 63) / 64) * 64; // entries per upload piece (512 B multiple)
     if (x_host)
     {
         for (int k = 0; k < NX; k++)
         {
-            const int64_t a = (int64_t)k * xchunk, b = a + xchunk < A->cols ? a + xchunk : A->cols;
+            const int64_t a = xlo + (int64_t)k * xchunk, b = a + xchunk < xhi ? a + xchunk : xhi;
             if (b > a)
                 cudaMemcpyAsync(A->d_x + a, x_host + a, sizeof(double) * (size_t)(b - a), cudaMemcpyHostToDevice, R.up[k % NS]);
             cudaEventRecord(R.x_ready[k], R.up[k % NS]);
@@ -1117,9 +1140,9 @@ static int csr_mult_pipelined(smvp_csr *A, const double *x_host, double *y_host,
     int waited = -1; // last upload piece the compute stream already waits for
     for (int c = 0; c < NR && rc == SMVP_OK; c++)
     {
-        if (x_host && A->pipe_xneed[c] > 0)
+        if (x_host && A->pipe_xneed[c] > xlo)
         {
-            int k = (int)(((int64_t)A->pipe_xneed[c] - 1) / xchunk);
+            int k = (int)(((int64_t)A->pipe_xneed[c] - 1 - xlo) / xchunk);
             k = k < NX ? k : NX - 1;
             for (; waited < k; waited++) // pieces alternate over NS streams: wait for each one up to k
                 cudaStreamWaitEvent(0, R.x_ready[waited + 1], 0);

@@ -307,9 +307,15 @@ class RowBlockCsr:
                 "exchange overlaps step k+1's SpMV, the pipe is drained inside the timed region"),
                "none": "kept local"}[exchange if world > 1 else "none"]
         self.partition_desc = "row blocks balanced by nnz, %d ranks; x replicated; y %s" % (world, how)
-        self.e2e_api = ("smvp_csr_mult(A, x_host, y_host, iters=1) [C ABI, pinned host buffers]" if world == 1 else
-                        "H2D of each rank's 1/N slice of x -> NCCL all-gather of x -> smvp_csr_mult_device -> %s -> D2H of "
-                        "each rank's y block" % how)
+        if world == 1:
+            self.e2e_api = "smvp_csr_mult(A, x_host, y_host, iters=1) [C ABI, pinned host buffers]"
+        elif os.environ.get("SMVP_E2E_MODE", "window") == "window":
+            self.e2e_api = ("every rank: smvp_csr_mult(A_block, x_host, y_host_block, iters=1) [C ABI, pinned host buffers]; the "
+                            "pipelined pass uploads only the window of x the row block reads and downloads the block's rows; "
+                            "the host holds all of y, no device-side exchange of y on this path")
+        else:
+            self.e2e_api = ("H2D of each rank's 1/N slice of x -> NCCL all-gather of x -> smvp_csr_mult_device -> %s -> D2H of "
+                            "each rank's y block" % how)
         self.x = None
         self._source_desc = source.desc
 
@@ -405,9 +411,24 @@ class RowBlockCsr:
                                              None, self.variant)
             if rc != 0:
                 raise self.eng.SmvpError(rc, "smvp_csr_mult")
+        elif os.environ.get("SMVP_E2E_MODE", "window") == "window":
+            # every rank makes the reference-facing C-ABI call on ITS row block with the whole host vector: the
+            # pipelined pass uploads only the window of x the block reads (for a banded matrix 1/N of the vector plus
+            # the band; a block that reads every column uploads all of it), multiplies tile range by tile range as the
+            # window arrives, and sends each finished range of its rows down to the host.  The host ends up with all
+            # of y, one block per rank; the device-side exchange of y is not part of this path (nothing on the
+            # devices consumes y here).
+            base = hy.data_ptr()
+            for g, A in enumerate(self.subs):
+                off = 8 * (self.sub_bounds[g] - self.r0)
+                rc = self.eng.lib().smvp_csr_mult(A._h, ctypes.c_void_p(hx.data_ptr()), ctypes.c_void_p(base + off), 1, None,
+                                                 self.variant)
+                if rc != 0:
+                    raise self.eng.SmvpError(rc, "smvp_csr_mult")
         else:
-            # every rank uploads only ITS 1/N slice of x over PCIe (the host vector crosses the bus once per step,
-            # job-wide) and the slices are all-gathered over NVLink, which is an order of magnitude faster
+            # SMVP_E2E_MODE=slices: every rank uploads only ITS 1/N slice of x over PCIe (the host vector crosses the
+            # bus once per step, job-wide), the slices are all-gathered over NVLink, then the device step with its
+            # exchange of y, then every rank downloads its block
             import torch
             import torch.distributed as dist
 

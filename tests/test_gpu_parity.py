@@ -335,8 +335,8 @@ def test_host_call_pipelined_transfers(eng, monkeypatch, banded):
 def test_host_call_pipelined_degenerate_shapes(eng):
     """Shapes on which the pipelined host pass has little to pipeline: a tall matrix with 3 columns (x is one upload
     piece), a wide one with 4 rows (one tile range holds everything, the others are empty), a big matrix without a
-    single nonzero (no range reads x), and one whose FIRST row already reads the last column (every range waits
-    for all of x)."""
+    single nonzero (no range reads x), one whose FIRST row already reads the last column (every range waits
+    for all of x), and one that reads only a window in the middle of x (the upload starts at the smallest column)."""
     rng = np.random.default_rng(41)
     big = (1 << 21) + 777
     cases = []
@@ -346,6 +346,7 @@ def test_host_call_pipelined_degenerate_shapes(eng):
     cases.append((4, big, rng.integers(0, 4, len(c)), c))                         # wide
     cases.append((big, big, np.zeros(0, np.int64), np.zeros(0, np.int64)))        # empty
     cases.append((big, big, np.concatenate([[0], r]), np.concatenate([[big - 1], np.maximum(r - 1, 0)])))  # first row reaches the end
+    cases.append((big, 3 * big, r, big + 100 + (r * 7) % (big - 5000)))           # only a window of x is read (a GPU's row block)
     for m, n, rows, cols in cases:
         key = np.unique(np.asarray(rows, np.int64) * n + np.asarray(cols, np.int64))
         coo = oracle.make_coo(key // n, key % n, rng.uniform(-1, 1, len(key)))
