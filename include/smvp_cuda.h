@@ -86,7 +86,9 @@ int smvp_tjds_build(const smvp_coo *coo, int32_t rows, int32_t cols, int64_t nnz
  * ms_each (may be NULL) receives `iters` per-iteration device times in milliseconds, taken with CUDA
  * events around the multiply only; the zero-fill of y is outside the bracket, as in the reference
  * (main-cli.c:405 vs :408/:419).  x is copied to the device once and y copied back once per call
- * (the reference reports the last iteration's y).
+ * (the reference reports the last iteration's y).  For vectors of millions of entries smvp_csr_mult overlaps
+ * both copies with the first / last pass, and uploads only the part of x between the smallest and the largest
+ * column index the matrix holds (the rest is never read): page-locked host buffers make the overlap effective.
  * smvp_tjds_mult: diag_limit <= 0 walks every jagged diagonal.  diag_limit = k > 0 walks only the
  * first k (and, like the shipped loop, skips a final diagonal that holds a single element): with
  * k = smvp_tjds_info().ref_diag_limit this reproduces the reference's golden TJDS report files,
