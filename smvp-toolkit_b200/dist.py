@@ -307,15 +307,7 @@ class RowBlockCsr:
                 "exchange overlaps step k+1's SpMV, the pipe is drained inside the timed region"),
                "none": "kept local"}[exchange if world > 1 else "none"]
         self.partition_desc = "row blocks balanced by nnz, %d ranks; x replicated; y %s" % (world, how)
-        if world == 1:
-            self.e2e_api = "smvp_csr_mult(A, x_host, y_host, iters=1) [C ABI, pinned host buffers]"
-        elif os.environ.get("SMVP_E2E_MODE", "window") == "window":
-            self.e2e_api = ("every rank: smvp_csr_mult(A_block, x_host, y_host_block, iters=1) [C ABI, pinned host buffers]; the "
-                            "pipelined pass uploads only the window of x the row block reads and downloads the block's rows; "
-                            "the host holds all of y, no device-side exchange of y on this path")
-        else:
-            self.e2e_api = ("H2D of each rank's 1/N slice of x -> NCCL all-gather of x -> smvp_csr_mult_device -> %s -> D2H of "
-                            "each rank's y block" % how)
+        self._exchange_how = how
         self.x = None
         self._source_desc = source.desc
 
@@ -402,6 +394,27 @@ class RowBlockCsr:
         self.multiply(stream)
         self.exchange_y(stream)
 
+    @property
+    def e2e_api(self):
+        """What one end-to-end step does (read after the steps: the mode may depend on the plan the library chose)."""
+        if self.world == 1:
+            return "smvp_csr_mult(A, x_host, y_host, iters=1) [C ABI, pinned host buffers]"
+        if self._e2e_mode() == "window":
+            return ("every rank: smvp_csr_mult(A_block, x_host, y_host_block, iters=1) [C ABI, pinned host buffers]; the "
+                    "pipelined pass uploads only the window of x the row block reads and downloads the block's rows; "
+                    "the host holds all of y, no device-side exchange of y on this path")
+        return ("H2D of each rank's 1/N slice of x -> NCCL all-gather of x -> smvp_csr_mult_device -> %s -> D2H of "
+                "each rank's y block" % self._exchange_how)
+
+    def _e2e_mode(self):
+        """"window": the host call per rank (uploads the window of x the block reads); "slices": 1/N slice per rank +
+        all-gather.  A relabelled block belongs to a power-law matrix and reads (nearly) every column: its window is
+        the whole vector, so the slices scheme moves N times less over PCIe there."""
+        forced = os.environ.get("SMVP_E2E_MODE")
+        if forced in ("window", "slices"):
+            return forced
+        return "slices" if self.A.x_relabel == 1 else "window"
+
     def e2e_step(self, hx, hy, stream):
         import ctypes
 
@@ -411,7 +424,7 @@ class RowBlockCsr:
                                              None, self.variant)
             if rc != 0:
                 raise self.eng.SmvpError(rc, "smvp_csr_mult")
-        elif os.environ.get("SMVP_E2E_MODE", "window") == "window":
+        elif self._e2e_mode() == "window":
             # every rank makes the reference-facing C-ABI call on ITS row block with the whole host vector: the
             # pipelined pass uploads only the window of x the block reads (for a banded matrix 1/N of the vector plus
             # the band; a block that reads every column uploads all of it), multiplies tile range by tile range as the
