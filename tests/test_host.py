@@ -319,3 +319,36 @@ def test_report_writer_threaded_vector_is_byte_identical(host, tmp_path, monkeyp
     assert len(got) == rows
     for i in list(range(0, 3000)) + list(range(rows - 50, rows)):
         assert got[i] == ("%g" % y[i]), i
+
+
+def test_threaded_loader_values_are_correctly_rounded(host, tmp_path, monkeypatch):
+    """200 000 random decimal tokens (1..25 significant digits, dot anywhere, exponents up to +-320, signs, leading and
+    trailing zeros) through the chunked parser: every value must be the correctly rounded double, i.e. what Python's
+    float() -- and strtod, which the reference's fscanf("%lg") uses -- returns for the same text."""
+    import random
+
+    rnd = random.Random(1234)
+    toks = []
+    for i in range(200000):
+        nd = rnd.randint(1, 25) if i % 3 else rnd.randint(1, 15)
+        digits = "".join(rnd.choice("0123456789") for _ in range(nd))
+        dot = rnd.randint(0, nd)
+        t = digits[:dot] + ("." if rnd.random() < 0.8 else "") + digits[dot:] if dot < nd else digits + rnd.choice(["", "."])
+        if t.startswith("."):
+            t = rnd.choice(["", "0", "00"]) + t
+        r = rnd.random()
+        if r < 0.5:
+            t += rnd.choice("eE") + rnd.choice(["", "+", "-"]) + str(rnd.randint(0, 30 if i % 2 else 320))
+        toks.append(rnd.choice(["", "-", "+"]) + t)
+    m = n = 1000
+    lines = ["%d %d %s\n" % (i % m + 1, (7 * i) % n + 1, t) for i, t in enumerate(toks)]
+    path = str(tmp_path / "tokens.mtx")
+    _write_mtx(path, "real", m, n, lines)
+    want = np.array([float(t) for t in toks])
+    for threads in (1, 6):
+        _with_threads(monkeypatch, threads, min_chunk=4096)
+        rc, got = load(host, path)
+        assert rc == 0
+        v = got[2]["val"]
+        bad = np.nonzero(v.view(np.int64) != want.view(np.int64))[0]
+        assert len(bad) == 0, (threads, [(toks[i], v[i], want[i]) for i in bad[:5]])
