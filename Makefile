@@ -14,7 +14,7 @@ CFLAGS    := -O2 -std=gnu11 -Wall -Wextra -D_XOPEN_SOURCE=700 -Iinclude -I$(PKG)
 
 CU_SRCS   := $(wildcard $(PKG)/csrc/*.cu)
 CU_OBJS   := $(patsubst $(PKG)/csrc/%.cu,$(OBJ)/%.o,$(CU_SRCS))
-HOST_LIB  := $(PKG)/host/smvp_mmio.c $(PKG)/host/smvp_host.c
+HOST_LIB  := $(filter-out %/main-cli.c,$(wildcard $(PKG)/host/*.c))
 
 .PHONY: all oracle test clean
 all: $(LIB)/libsmvp_cuda.so $(LIB)/libsmvp_host.so $(LIB)/smvp-toolkit-cli

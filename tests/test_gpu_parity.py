@@ -426,16 +426,29 @@ def test_csr_relabel_forced_bit_identical(eng, monkeypatch):
         h.free()
 
 
-def test_csr_relabel_auto_decision(eng):
-    """AUTO relabels only when x is large AND the 4 Mi most popular columns hold most of the nonzeros (>= 1/2 and
-    >= 4x their fair share, which needs more than 16 Mi columns):
-    a power-law matrix qualifies, a uniform one of the same shape does not; results stay within 1e-12 either way.
-    The big-matrix host path (pipelined copy-out, whole-x upload + permutation) is exercised on the way."""
+def _hot_cold_coo(rng, m, n, nnz, hot_cols, hot_share):
+    """Unique (row, col) pairs: `hot_share` of the entries fall on `hot_cols` columns scattered over the whole index
+    range, the rest uniformly on all n columns."""
+    rows = rng.integers(0, m, nnz)
+    hot = (rng.integers(0, hot_cols, nnz) * 2654435761) % n
+    cols = np.where(rng.random(nnz) < hot_share, hot, rng.integers(0, n, nnz))
+    key = np.unique(rows * n + cols)
+    return oracle.make_coo(key // n, key % n, rng.uniform(-1, 1, len(key)))
+
+
+def test_csr_relabel_auto_decision(eng, monkeypatch):
+    """AUTO relabels only when the handle touches at least MIN distinct columns AND the HOT most popular ones hold most
+    of the nonzeros (>= 1/2 and >= 4x their fair share among the touched columns): a hot/cold matrix qualifies, a
+    uniform one of the same shape does not; results stay within 1e-12 either way.  (MIN / HOT are 8 Mi / 4 Mi columns;
+    the test scales them down through the tuning hooks.)  The big-matrix host path (pipelined copy-out, whole-x upload
+    + permutation) is exercised on the way."""
+    monkeypatch.setenv("SMVP_RELABEL_MIN_COLS", str(1 << 16))
+    monkeypatch.setenv("SMVP_RELABEL_HOT_COLS", str(1 << 15))
     rng = np.random.default_rng(78)
-    m, n, nnz = 1 << 20, (17 << 20) + 5, 6000000
+    m, n, nnz = 200000, 2000003, 3000000
     x = rng.uniform(-1, 1, n)
-    for power, expect in ((8.0, 1), (1.0, -1)):
-        coo = _powerlaw_coo(rng, m, n, nnz, power)
+    for hot_share, expect in ((0.7, 1), (0.0, -1)):
+        coo = _hot_cold_coo(rng, m, n, nnz, 1 << 14, hot_share)
         rp, ci, va = oracle.csr_build(coo, m, n)
         y_ref = oracle.csr_mult(rp, ci, va, x)
         A = eng.CsrMatrix.build(coo, m, n)
@@ -443,9 +456,35 @@ def test_csr_relabel_auto_decision(eng):
         for iters in (1, 2):
             y, _ = A.mult(x, iters=iters, variant=eng.CSR_MERGE)
             assert util.rel_l2(y, y_ref) <= TOL
-        assert A.x_relabel == expect, (power, A.x_relabel)
+        assert A.x_relabel == expect, (hot_share, A.x_relabel)
         g = A.export()
         assert np.array_equal(g[1], ci)
+        A.free()
+
+
+def test_csr_relabel_auto_keeps_banded_row_block(eng, monkeypatch):
+    """Round-1 misfire: the shard of one GPU out of 8 of a banded matrix reads a 1/8 window of
+    x; measured against ALL columns that window looked like a hot set and the block was relabelled.  The decision is
+    now taken over the columns the handle touches: a banded row block keeps its natural order (x_relabel == -1)
+    whatever the size of the column space around it.  Thresholds scaled down as above: the block touches 60 002 of
+    800 000 columns -- the old rule (fair share over all columns) relabelled exactly this shape."""
+    import torch
+
+    monkeypatch.setenv("SMVP_RELABEL_MIN_COLS", str(1 << 16))
+    monkeypatch.setenv("SMVP_RELABEL_HOT_COLS", str(1 << 15))
+    for m in (60000, 300000):  # below MIN touched columns; above it (then the hot set holds < 1/2 of a banded block)
+        n, r0 = 800000, 350000
+        rows = torch.arange(m, dtype=torch.int32, device="cuda").repeat_interleave(3)
+        cols = ((rows + r0).view(-1, 3) + torch.tensor([-1, 0, 1], dtype=torch.int32, device="cuda")).reshape(-1).contiguous()
+        vals = torch.tensor([-1.0, 26.0, -1.0], dtype=torch.float64, device="cuda").repeat(m)
+        A = eng.CsrMatrix.build_device(rows, cols, vals, m, n, 3 * m)
+        x = torch.ones(n, dtype=torch.float64, device="cuda")
+        y = torch.empty(m, dtype=torch.float64, device="cuda")
+        A.set_x_device(x)
+        A.mult_device(None, y, eng.CSR_MERGE)
+        torch.cuda.synchronize()
+        assert A.x_relabel == -1, m
+        assert bool((y == 24.0).all())
         A.free()
 
 
