@@ -155,6 +155,13 @@ typedef struct smvp_tjds_info_t
     int32_t y_relabel;        /* multiply plan: 1 = the kernels scatter through popularity-relabelled row
                                  indices and a last pass restores the row order of y, -1 = natural order,
                                  0 = not decided yet (decided at the first pass)                  */
+    int32_t skewed_walk;      /* multiply plan: 1 = the kernels walk the (slot, diagonal) plane along anti-diagonals and
+                                 merge runs of equal rows in registers before reducing into y (banded matrices),
+                                 -1 = straight walk, 0 = not decided yet                              */
+    int32_t det_route;        /* SMVP_TJDS_DETERMINISTIC with the current x: 1 = exact integer accumulation,
+                                 -1 = served by the atomic kernel because x or the matrix holds Inf / NaN or the
+                                 exponents may overflow (results then follow IEEE propagation, not run-to-run
+                                 bit identity), 0 = not decided yet                                   */
 } smvp_tjds_info_t;
 
 int smvp_csr_info(const smvp_csr *A, smvp_csr_info_t *out);

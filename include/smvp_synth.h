@@ -59,6 +59,14 @@ int smvp_copy_device(void *d_dst, const void *d_src, int64_t bytes, void *stream
  * when dst is a multicast mapping, where coalesced SM stores move data faster than a copy-engine transfer */
 int smvp_push_device(void *d_dst, const void *d_src, int64_t bytes, int ctas, void *stream);
 
+/* the same with n_dst (<= 8) destinations: the source is read once and stored to every destination (the unicast
+ * all-gather of one rank's block of y into its peers' buffers).  d_dst_list is a HOST array of device pointers. */
+int smvp_push_fanout_device(void *const *d_dst_list, int n_dst, const void *d_src, int64_t bytes, int ctas, void *stream);
+
+/* out[i] = (((p_0[i] + p_1[i]) + p_2[i]) + ...) with p_k = d_parts + k * stride: the fixed-order combine of per-rank
+ * partial results (column-block TJDS), bit-identical whatever order the parts arrived in */
+int smvp_sum_ordered_device(double *d_out, const double *d_parts, int nparts, int64_t stride, int64_t n, void *stream);
+
 /* L2 flush helper for timing hygiene: writes `bytes` of a scratch buffer owned by the library */
 int smvp_flush_l2(int64_t bytes, void *stream);
 

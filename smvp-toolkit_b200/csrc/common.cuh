@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <atomic>
 #include <cstdlib>
+#include <functional>
 #include <new>
 
 #include "../../include/smvp_cuda.h"
@@ -52,6 +53,41 @@ static inline cudaError_t dev_alloc(T **p, int64_t n)
     bytes = ((bytes + 255) & ~(size_t)255) + 256;
     return cudaMalloc((void **)p, bytes);
 }
+
+// a device temporary that is released on every exit path (error returns included)
+struct DevTmp
+{
+    void *p = nullptr;
+    DevTmp() = default;
+    DevTmp(const DevTmp &) = delete;
+    DevTmp &operator=(const DevTmp &) = delete;
+    ~DevTmp() { cudaFree(p); }
+    template <typename T>
+    cudaError_t alloc(int64_t n)
+    {
+        cudaFree(p);
+        p = nullptr;
+        T *q = nullptr;
+        const cudaError_t e = dev_alloc(&q, n);
+        p = q;
+        return e;
+    }
+    template <typename T>
+    T *as() const { return static_cast<T *>(p); }
+};
+
+// The `-n` loop of the host entry points (main-cli.c:402-420 / :1004-1024): `iters` passes, per-iteration
+// milliseconds into ms_each (may be NULL).  `pass(stream)` enqueues ONE pass.
+//   exact mode   CUDA events around every pass and a synchronisation per iteration (what round 1 did everywhere);
+//   batched mode for matrices whose pass is shorter than the launch + synchronisation latency that exact mode adds
+//                (~10 us): the first pass is timed exactly, the others are captured `batch` at a time in a CUDA graph
+//                and replayed back to back; a pass is charged its batch's time / batch.  SMVP_EXACT_ITER_TIMES=1
+//                forces exact mode, SMVP_LOOP_BATCH sets the batch (default 50).
+constexpr int64_t SMVP_SMALL_LOOP_ITEMS = 1 << 22; // rows + cols + nnz below this: batched mode
+//                `multi(stream, n)`, when given, enqueues n passes as ONE launch (tiny matrices: a single CTA loops
+//                over the passes, csr_tiny_loop_kernel) and replaces the graph.
+int timed_loop(int iters, double *ms_each, bool batched, const std::function<int(cudaStream_t)> &pass,
+               const std::function<int(cudaStream_t, int)> &multi = nullptr);
 
 struct DeviceProps
 {
@@ -166,6 +202,14 @@ struct smvp_tjds
     int32_t *x_exp;          // [1] exponent bound of max |x|
     double *d_x, *d_y;
     // popularity relabelling of the ROW space (relabel.cu): 0 undecided, 1 in use, -1 not worth it
+    int32_t skew;            // walk of the multiply kernels: 0 undecided, 1 skewed (runs of equal rows), -1 straight
+    int32_t det_flags[3];    // host copy: [0] bit 0 = the matrix holds Inf/NaN, bit 1 = a row has entries but only zeros;
+                             // [1] / [2] = largest / smallest row_exp (EXP_NONE / EXP_LOW_NONE if none)
+    int32_t *x_exp_host;     // pinned: x_exp as of the last smvp_tjds_set_x_device, valid once x_exp_event has passed
+    cudaEvent_t x_exp_event;
+    int32_t x_exp_pending;   // 1: x_exp_host has not been looked at since the last set_x
+    int32_t det_fast;        // for the current x: 1 every row bound is in the range of the short split loop, -1 not
+    int32_t det_route;       // for the current x: 1 exact integer kernel, -1 atomic kernel (non-finite / overflowing input)
     int32_t relabel_state;
     int32_t *row_rel;        // [nnz]  rank of row_ind[j]; what the kernels scatter through when in use
     int32_t *row_rank;       // [rows] rank of row r

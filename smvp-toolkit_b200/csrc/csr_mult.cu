@@ -250,6 +250,38 @@ __global__ void __launch_bounds__(256) csr_vector_kernel(const int32_t *__restri
         store_y<FANOUT>(y, fan, row, sum);
 }
 
+// =====================================================================================  TINY LOOP
+// Matrices of a few thousand nonzeros (the reference's sample-data: ibm32 126, curtis54 291, pdp08-pg4 16): one pass
+// is far shorter than a kernel launch, so the `-n` loop itself moves onto the device.  ONE CTA repeats the whole
+// multiply `passes` times -- warp per row, lanes stride the row, __shfl_xor_sync fold, exactly the vector kernel's
+// arithmetic -- with a block barrier between passes.  The arrays are read with plain loads after each barrier (no
+// read-only promise), so every pass really re-reads row_ptr / col_ind / val / x (from L1) and re-writes y: work is
+// repeated, not hoisted.  Only reachable from the batched `-n` loop of smvp_csr_mult.
+constexpr int TINY_THREADS = 512;
+constexpr int64_t TINY_MAX_NNZ = 16384;
+constexpr int32_t TINY_MAX_ROWS = 4096;
+__global__ void __launch_bounds__(TINY_THREADS) csr_tiny_loop_kernel(const int32_t *row_ptr, const int32_t *col_ind, const double *val,
+                                                                     const double *x, double *y, int32_t rows, int passes)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int p = 0; p < passes; p++)
+    {
+        for (int32_t row = warp; row < rows; row += TINY_THREADS / 32)
+        {
+            const int32_t start = row_ptr[row], end = row_ptr[row + 1];
+            double sum = 0.0;
+            for (int32_t j = start + lane; j < end; j += 32)
+                sum = __dadd_rn(sum, __dmul_rn(val[j], x[col_ind[j]]));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                sum = __dadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+            if (lane == 0)
+                y[row] = sum;
+        }
+        __syncthreads(); // pass boundary: also a compiler barrier, the next pass reloads everything
+    }
+}
+
 // the column indices the multiply kernels read: the relabelled copy when that plan is in use (relabel.cu)
 static inline const int32_t *mult_cols(const smvp_csr *A) { return A->relabel_state == 1 ? A->col_rel : A->col_ind; }
 
@@ -1215,42 +1247,73 @@ extern "C" int smvp_csr_mult(smvp_csr *A, const double *x_host, double *y_host, 
     if (relabeled) // once, before the loop, as the reference permutes x for TJDS (main-cli.c:907-923)
         SMVP_TRY(csr_relabel_x(A, A->d_x, 0));
     const double *xm = relabeled ? A->x_rel : A->d_x;
-    cudaEvent_t e0, e1;
-    SMVP_CUDA(cudaEventCreate(&e0));
-    SMVP_CUDA(cudaEventCreate(&e1));
     bool y_copied = false;
-    for (int it = 0; it < iters && rc == SMVP_OK; it++)
+    // y is zero-filled outside the timed passes (main-cli.c:405); both kernels write every row, the fill only keeps
+    // the reference's structure observable
+    if (A->rows > 0)
+        SMVP_CUDA(cudaMemsetAsync(A->d_y, 0, sizeof(double) * (size_t)A->rows, 0));
+    if (!pipelined)
     {
-        // y is zero-filled outside the bracket (main-cli.c:405); both kernels write every row, the
-        // fill only keeps the reference's structure observable
-        cudaMemsetAsync(A->d_y, 0, sizeof(double) * (size_t)A->rows, 0);
-        float ms = 0.f;
-        const bool first = it == 0, last = it == iters - 1;
-        if (pipelined && ((first && upload_under_pass) || last))
-        {
-            rc = csr_mult_pipelined(A, (first && upload_under_pass) ? x_host : nullptr, last ? y_host : nullptr, &ms);
-            y_copied = last && rc == SMVP_OK;
-        }
-        else
-        {
-            cudaEventRecord(e0, 0);
-            rc = csr_mult_launch(A, xm, A->d_y, nullptr, variant, 0);
-            cudaEventRecord(e1, 0);
-            if (rc != SMVP_OK)
-                break;
-            cudaError_t e = cudaEventSynchronize(e1);
-            if (e != cudaSuccess)
-            {
-                rc = cuda_fail(e, "cudaEventSynchronize", __FILE__, __LINE__);
-                break;
-            }
-            cudaEventElapsedTime(&ms, e0, e1);
-        }
-        if (ms_each && rc == SMVP_OK)
-            ms_each[it] = (double)ms;
+        // small matrices: a pass is shorter than a launch + synchronisation, so the loop runs batched in CUDA graphs
+        const bool small = (int64_t)A->rows + A->cols + A->nnz < SMVP_SMALL_LOOP_ITEMS;
+        // (an explicitly requested variant is honoured pass by pass; AUTO may pick the looping kernel)
+        const bool tiny = variant == SMVP_CSR_AUTO && A->nnz <= TINY_MAX_NNZ && A->rows <= TINY_MAX_ROWS &&
+                          getenv("SMVP_NO_TINY_LOOP") == nullptr;
+        std::function<int(cudaStream_t, int)> multi;
+        if (tiny)
+            multi = [&](cudaStream_t s, int n) {
+                SMVP_LAUNCH(csr_tiny_loop_kernel, 1, TINY_THREADS, 0, s, (const int32_t *)A->row_ptr, mult_cols(A), (const double *)A->val,
+                            xm, A->d_y, A->rows, n);
+                SMVP_CUDA(cudaGetLastError());
+                return (int)SMVP_OK;
+            };
+        if (A->rows > 0)
+            rc = timed_loop(iters, ms_each, small, [&](cudaStream_t s) { return csr_mult_launch(A, xm, A->d_y, nullptr, variant, s); },
+                            multi);
+        else if (ms_each)
+            for (int it = 0; it < iters; it++)
+                ms_each[it] = 0.0;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    else
+    {
+        cudaEvent_t e0, e1;
+        SMVP_CUDA(cudaEventCreate(&e0));
+        cudaError_t ce = cudaEventCreate(&e1);
+        if (ce != cudaSuccess)
+        {
+            cudaEventDestroy(e0);
+            return cuda_fail(ce, "cudaEventCreate", __FILE__, __LINE__);
+        }
+        for (int it = 0; it < iters && rc == SMVP_OK; it++)
+        {
+            float ms = 0.f;
+            const bool first = it == 0, last = it == iters - 1;
+            if ((first && upload_under_pass) || last)
+            {
+                rc = csr_mult_pipelined(A, (first && upload_under_pass) ? x_host : nullptr, last ? y_host : nullptr, &ms);
+                y_copied = last && rc == SMVP_OK;
+            }
+            else
+            {
+                cudaEventRecord(e0, 0);
+                rc = csr_mult_launch(A, xm, A->d_y, nullptr, variant, 0);
+                cudaEventRecord(e1, 0);
+                if (rc != SMVP_OK)
+                    break;
+                const cudaError_t e = cudaEventSynchronize(e1);
+                if (e != cudaSuccess)
+                {
+                    rc = cuda_fail(e, "cudaEventSynchronize", __FILE__, __LINE__);
+                    break;
+                }
+                cudaEventElapsedTime(&ms, e0, e1);
+            }
+            if (ms_each && rc == SMVP_OK)
+                ms_each[it] = (double)ms;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
     if (rc != SMVP_OK)
         return rc;
     if (A->rows > 0 && !y_copied)

@@ -168,10 +168,69 @@ __global__ void __launch_bounds__(256) vector_add_kernel(double *__restrict__ y,
 __global__ void __launch_bounds__(512) push_kernel(double2 *__restrict__ dst, const double2 *__restrict__ src, int64_t n16,
                                                    double *__restrict__ dst_tail, const double *__restrict__ src_tail, int tail)
 {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) // four independent loads in flight per thread
+    {
+        const double2 a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+        dst[i] = a;
+        dst[i + stride] = b;
+        dst[i + 2 * stride] = c;
+        dst[i + 3 * stride] = d;
+    }
+    for (; i < n16; i += stride)
         dst[i] = src[i];
     if (blockIdx.x == 0 && (int)threadIdx.x < tail)
         dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+
+// the same with up to 8 destinations: src is read once, every 16-byte piece is stored to each destination (peer
+// mappings of a symmetric-memory buffer: the unicast all-gather of one rank's block)
+struct PushFan
+{
+    double2 *dst[8];
+    double *dst_tail[8];
+    int n;
+};
+__global__ void __launch_bounds__(512) push_fanout_kernel(const __grid_constant__ PushFan fan, const double2 *__restrict__ src, int64_t n16,
+                                                          const double *__restrict__ src_tail, int tail)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) // four independent loads in flight per thread
+    {
+        const double2 a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+        for (int k = 0; k < fan.n; k++)
+        {
+            fan.dst[k][i] = a;
+            fan.dst[k][i + stride] = b;
+            fan.dst[k][i + 2 * stride] = c;
+            fan.dst[k][i + 3 * stride] = d;
+        }
+    }
+    for (; i < n16; i += stride)
+    {
+        const double2 a = src[i];
+        for (int k = 0; k < fan.n; k++)
+            fan.dst[k][i] = a;
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < tail)
+        for (int k = 0; k < fan.n; k++)
+            fan.dst_tail[k][threadIdx.x] = src_tail[threadIdx.x];
+}
+
+// out[i] = (((p_0[i] + p_1[i]) + p_2[i]) + ...), p_k = parts + k * stride: the fixed-order combine of per-rank partial
+// results (column-block TJDS): the same bits whatever order the parts arrived in
+__global__ void __launch_bounds__(256) sum_ordered_kernel(double *__restrict__ out, const double *__restrict__ parts, int nparts,
+                                                          int64_t stride, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    {
+        double acc = parts[i];
+        for (int k = 1; k < nparts; k++)
+            acc = __dadd_rn(acc, parts[(int64_t)k * stride + i]);
+        out[i] = acc;
+    }
 }
 
 static inline unsigned grid_for(int64_t n, int per_thread = 4)
@@ -386,6 +445,60 @@ extern "C" int smvp_push_device(void *d_dst, const void *d_src, int64_t bytes, i
     SMVP_LAUNCH(push_kernel, (unsigned)ctas, 512, 0, (cudaStream_t)stream, (double2 *)(dst + head), (const double2 *)(src + head), n16,
                 (double *)(dst + head + 16 * n16), (const double *)(src + head + 16 * n16), tail);
     SMVP_CUDA(cudaGetLastError());
+    return SMVP_OK;
+}
+
+extern "C" int smvp_push_fanout_device(void *const *d_dst_list, int n_dst, const void *d_src, int64_t bytes, int ctas, void *stream)
+{
+    if (bytes < 0 || ctas < 1 || (bytes % 8) != 0 || n_dst < 1 || n_dst > 8 || !d_dst_list || (bytes > 0 && !d_src))
+        return SMVP_E_ARG;
+    if (bytes == 0)
+        return SMVP_OK;
+    const char *src = (const char *)d_src;
+    bool aligned = true;
+    for (int k = 0; k < n_dst; k++)
+    {
+        if (!d_dst_list[k])
+            return SMVP_E_ARG;
+        aligned = aligned && ((((uintptr_t)d_dst_list[k]) & 15) == (((uintptr_t)src) & 15));
+    }
+    if (!aligned) // mutually misaligned: one copy-engine transfer per destination
+    {
+        for (int k = 0; k < n_dst; k++)
+            SMVP_TRY(smvp_copy_device(d_dst_list[k], d_src, bytes, stream));
+        return SMVP_OK;
+    }
+    int64_t head = (((uintptr_t)src) & 15) ? 8 : 0;
+    if (head > bytes)
+        head = bytes;
+    PushFan fan;
+    fan.n = n_dst;
+    const int64_t body = bytes - head;
+    const int64_t n16 = body / 16;
+    const int tail = (int)((body % 16) / 8);
+    for (int k = 0; k < 8; k++)
+    {
+        char *dst = k < n_dst ? (char *)d_dst_list[k] : nullptr;
+        fan.dst[k] = (double2 *)(dst ? dst + head : nullptr);
+        fan.dst_tail[k] = (double *)(dst ? dst + head + 16 * n16 : nullptr);
+        if (dst && head)
+            SMVP_CUDA(cudaMemcpyAsync(dst, src, (size_t)head, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
+    SMVP_LAUNCH(push_fanout_kernel, (unsigned)ctas, 512, 0, (cudaStream_t)stream, fan, (const double2 *)(src + head), n16,
+                (const double *)(src + head + 16 * n16), tail);
+    SMVP_CUDA(cudaGetLastError());
+    return SMVP_OK;
+}
+
+extern "C" int smvp_sum_ordered_device(double *d_out, const double *d_parts, int nparts, int64_t stride, int64_t n, void *stream)
+{
+    if (n < 0 || nparts < 1 || stride < 0 || (n > 0 && (!d_out || !d_parts)))
+        return SMVP_E_ARG;
+    if (n > 0)
+    {
+        SMVP_LAUNCH(sum_ordered_kernel, grid_for(n), 256, 0, (cudaStream_t)stream, d_out, d_parts, nparts, stride, n);
+        SMVP_CUDA(cudaGetLastError());
+    }
     return SMVP_OK;
 }
 

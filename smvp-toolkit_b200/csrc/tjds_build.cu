@@ -96,6 +96,10 @@ void tjds_release(smvp_tjds *A)
     cudaFree(A->row_exp);
     cudaFree(A->acc);
     cudaFree(A->x_exp);
+    if (A->x_exp_host)
+        cudaFreeHost(A->x_exp_host);
+    if (A->x_exp_event)
+        cudaEventDestroy(A->x_exp_event);
     cudaFree(A->d_x);
     cudaFree(A->d_y);
     tjds_relabel_release(A);

@@ -76,6 +76,35 @@ def allgather_v(dist, y_full, bounds, rank):
                 dist.broadcast(v, src=g)
 
 
+def allgather_padded(dist, y_pad, y_full, bounds, rank, per):
+    """All-gather of uneven blocks through ONE NCCL all_gather_into_tensor on equal padded slots (block g lives in
+    y_pad[g*per : g*per + rows_g]), followed by the compaction into the contiguous y_full.  This is the NCCL baseline the
+    fused exchanges are compared with (round 1 used dist.all_gather on a list of uneven views, which makes torch stage
+    through a temporary: a straw man)."""
+    dist.all_gather_into_tensor(y_pad, y_pad[rank * per:(rank + 1) * per])
+    for g in range(len(bounds) - 1):
+        n = bounds[g + 1] - bounds[g]
+        if n > 0:
+            y_full[bounds[g]:bounds[g + 1]].copy_(y_pad[g * per:g * per + n], non_blocking=True)
+
+
+def reduce_scatter_ordered(dist, eng, y_owned, y_partial, scratch, rank, world, stream=None):
+    """y_owned = block `rank` of the sum over ranks of y_partial, added in RANK ORDER by our own kernel
+    (smvp_sum_ordered_device) after an all-to-all of the blocks: the bits do not depend on NCCL's algorithm, protocol or
+    channel count, which is what makes the deterministic TJDS variant reproducible run to run at N > 1."""
+    per = y_owned.numel()
+    if dist.get_backend() == "nccl":
+        dist.all_to_all_single(scratch, y_partial)
+        eng.sum_ordered_device(y_owned, scratch, world, per, per, stream)
+    else:  # gloo (CPU tests) has no all-to-all: gather every partial, add my block in rank order
+        parts = [y_partial.new_empty(y_partial.shape) for _ in range(world)]
+        dist.all_gather(parts, y_partial)
+        acc = parts[0][rank * per:(rank + 1) * per].clone()
+        for k in range(1, world):
+            acc = acc + parts[k][rank * per:(rank + 1) * per]
+        y_owned.copy_(acc)
+
+
 def reduce_scatter_sum(dist, y_owned, y_partial, rank):
     """y_owned = block `rank` of sum over ranks of y_partial (len(y_partial) == world * len(y_owned))."""
     if dist.get_backend() == "nccl":
@@ -94,16 +123,20 @@ def row_block_spmv(dist, local_mult, bounds, rank, x, y_full):
     return y_full
 
 
-def col_block_spmv(dist, local_mult, bounds, rank, world, x, rows):
+def col_block_spmv(dist, local_mult, bounds, rank, world, x, rows, ordered=False, eng=None):
     """The column-partitioned product, backend-agnostic: partial = local_mult(x[my columns]) has `rows`
-    entries on every rank; the partials are summed and scattered (rank g owns rows [g*p, (g+1)*p))."""
+    entries on every rank; the partials are summed and scattered (rank g owns rows [g*p, (g+1)*p)).
+    ordered=True: the sum is taken in rank order (reduce_scatter_ordered) instead of by the backend's reduction."""
     import torch
 
     per = -(-rows // world)
     partial = torch.zeros(per * world, dtype=torch.float64, device=x.device)
     partial[:rows] = local_mult(x[bounds[rank]:bounds[rank + 1]])
     owned = torch.zeros(per, dtype=torch.float64, device=x.device)
-    reduce_scatter_sum(dist, owned, partial, rank)
+    if ordered:
+        reduce_scatter_ordered(dist, eng, owned, partial, torch.empty_like(partial), rank, world)
+    else:
+        reduce_scatter_sum(dist, owned, partial, rank)
     return owned
 
 
@@ -228,7 +261,9 @@ class RowBlockCsr:
         self.symm = None
         self.y_fan = None
         self.peer_views, self.copy_stream, self.sub_events = None, None, None
-        self.mc_base, self.y_src = None, None
+        self.y_src, self.y_pad = None, None
+        self.scheme, self.tuning = None, None
+        self.spmv_events = None  # (start, end) CUDA events around the SpMV launch of the step in progress
         self.nbuf, self.k = 1, 0
         if world > 1 and exchange in ("multicast", "p2p", "copy", "pipeline"):
             import torch.distributed as dist
@@ -241,33 +276,17 @@ class RowBlockCsr:
             self.y_full = self.y_sym[:self.M]
             self.symm = symm_mem.rendezvous(self.y_sym, dist.group.WORLD.group_name)
             self.y_write = None
+            self.mc_base = int(self.symm.multicast_ptr) if self.symm.multicast_ptr else None
+            self.peer_ranks = [(rank + j) % world for j in range(1, world)]  # ring order
             if exchange == "multicast":
-                if not self.symm.multicast_ptr:
+                if not self.mc_base:
                     raise RuntimeError("this system exposes no NVSwitch multicast mapping; use exchange='p2p' or 'nccl'")
                 # write-only view of y: one store here lands in every rank's y_full
-                self.y_write = int(self.symm.multicast_ptr) + 8 * self.r0
-            elif (exchange == "pipeline" and self.symm.multicast_ptr and
-                  os.environ.get("SMVP_PIPELINE_MODE", "multicast" if world >= 8 else "unicast") == "multicast"):
-                # one copy-engine transfer per step to the NVSwitch multicast address: the switch replicates my rows
-                # into every rank's y (my own included), so egress is 1/N of the vector instead of (N-1)/N.
-                # Measured on B200 (profiles/r01_multigpu.md): N=8 0.72 ms vs 0.83 ms with 7 peer copies, but N=4 1.05 vs
-                # 0.85 ms and N=2 1.91 vs 1.62 ms (a multicast copy moves data at about half the rate of a peer copy),
-                # hence the switch-over at 8 ranks.
-                self.mc_base = int(self.symm.multicast_ptr)
-                self.y_src = [torch.zeros(self.r1 - self.r0, dtype=torch.float64, device="cuda") for _ in range(self.nbuf)]
-                # the push is done by a small high-priority SM kernel (SMVP_PUSH_CTAS CTAs, 128-bit stores) rather than
-                # the copy engines: measured at 8 ranks 0.661 ms/step with 32 CTAs vs 0.708 ms with a copy-engine transfer
-                # (gpurun_out bench_n8_push32.json / bench_n8_final.json).  SMVP_PUSH_CTAS=0 selects the copy engines.
-                self.push_ctas = int(os.environ.get("SMVP_PUSH_CTAS", "32"))
-                self.copy_streams = [torch.cuda.Stream(priority=-1) if self.push_ctas > 0 else torch.cuda.Stream()]
-                self.copy_stream = self.copy_streams[0]
-                self.copy_done = [[torch.cuda.Event()] for _ in range(self.nbuf)]
-                self.sub_events = [[torch.cuda.Event()] for _ in range(self.nbuf)]
-                self.copy_pending = [False] * self.nbuf
-            elif exchange in ("copy", "pipeline"):
-                # peers in ring order (rank+1, rank+2, ...): at any moment every GPU receives from one sender only
-                ring = [(rank + j) % world for j in range(1, world)]
-                self.peer_views = [self.symm.get_buffer(k, (self.nbuf * self.M,), torch.float64) for k in ring]
+                self.y_write = self.mc_base + 8 * self.r0
+            elif exchange == "pipeline":
+                self._setup_pipeline()
+            elif exchange == "copy":
+                self.peer_views = [self.symm.get_buffer(k, (self.nbuf * self.M,), torch.float64) for k in self.peer_ranks]
                 # SMVP_COPY_STREAMS=1: one stream, the ring steps follow each other (a permutation per step);
                 # default: one stream per peer, all copies in flight at once
                 nstreams = int(os.environ.get("SMVP_COPY_STREAMS", "0")) or len(self.peer_views)
@@ -275,8 +294,6 @@ class RowBlockCsr:
                 self.copy_streams = [pool[i % len(pool)] for i in range(len(self.peer_views))]
                 self.copy_stream = self.copy_streams[0]
                 self.sub_events = [[torch.cuda.Event() for _ in self.subs] for _ in range(self.nbuf)]
-                self.copy_done = [[torch.cuda.Event() for _ in self.copy_streams] for _ in range(self.nbuf)]
-                self.copy_pending = [False] * self.nbuf
             else:
                 if world > 8:
                     raise RuntimeError("p2p fan-out supports at most 8 ranks")
@@ -285,31 +302,164 @@ class RowBlockCsr:
                 order = [rank] + [k for k in range(world) if k != rank]
                 self.y_fan = [ptrs[k] + 8 * self.r0 for k in order]
         else:
-            self.y_full = torch.zeros(self.M, dtype=torch.float64, device="cuda")
             self.y_write = None
-        self.y_local = self.y_full[self.r0:self.r1]
+            if world > 1 and exchange == "nccl":
+                # equal padded slots for ONE all_gather_into_tensor; the SpMV writes straight into my slot
+                self.per = max(self.bounds[g + 1] - self.bounds[g] for g in range(world))
+                self.y_pad = torch.zeros(self.per * world, dtype=torch.float64, device="cuda")
+            self.y_full = torch.zeros(self.M, dtype=torch.float64, device="cuda")
+        if self.y_pad is not None:
+            self.y_local = self.y_pad[rank * self.per:rank * self.per + (self.r1 - self.r0)]
+        else:
+            self.y_local = self.y_full[self.r0:self.r1]
         self.local_rows_out = self.r1 - self.r0
         resolved = self.A.auto_variant if variant == eng.CSR_AUTO else variant
         self.variant_name = {eng.CSR_VECTOR: "vector", eng.CSR_MERGE: "merge"}[resolved]
         self.kernel_name = {"vector": "csr_vector_kernel", "merge": "csr_merge_warp_kernel"}[self.variant_name]
-        how = {"nccl": "all-gathered over NCCL", "multicast": "stored by the SpMV kernel to the NVSwitch multicast "
-               "address of y (fused, no collective) + device barrier",
+        self.x = None
+        self._source_desc = source.desc
+
+    # ------------------------------------------------------------------ pipelined exchange: schemes and their tuning
+    SCHEME_HOW = {
+        "ce_unicast": "the copy engines (one peer copy per rank)",
+        "ce_multicast": "ONE copy-engine transfer to the NVSwitch multicast address",
+        "sm_multicast": "a small high-priority SM kernel (%d CTAs, 128-bit stores) writing to the NVSwitch multicast address",
+        "sm_unicast": "a small high-priority SM kernel (%d CTAs) that reads my rows once and stores them into every peer's y",
+    }
+
+    def _setup_pipeline(self):
+        import torch
+
+        nloc = self.r1 - self.r0
+        self.y_src = [torch.zeros(nloc, dtype=torch.float64, device="cuda") for _ in range(self.nbuf)]
+        self.peer_views = [self.symm.get_buffer(k, (self.nbuf * self.M,), torch.float64) for k in self.peer_ranks]
+        self.peer_ptrs = [int(self.symm.buffer_ptrs[k]) for k in self.peer_ranks]
+        self.push_stream = torch.cuda.Stream(priority=-1)
+        self.ce_streams = [torch.cuda.Stream() for _ in self.peer_ranks]
+        self.spmv_done = [torch.cuda.Event() for _ in range(self.nbuf)]
+        self.copy_done = [torch.cuda.Event() for _ in range(self.nbuf)]
+        self.copy_pending = [False] * self.nbuf
+        forced = os.environ.get("SMVP_PIPELINE_SCHEME")  # e.g. sm_multicast:32, ce_unicast
+        if forced is None and os.environ.get("SMVP_PIPELINE_MODE"):  # round-1 switches, still honoured
+            ctas = int(os.environ.get("SMVP_PUSH_CTAS", "32"))
+            forced = ("ce_unicast" if os.environ["SMVP_PIPELINE_MODE"] == "unicast" else
+                      ("sm_multicast:%d" % ctas if ctas > 0 else "ce_multicast"))
+        self.set_scheme(forced or ("sm_multicast:32" if (self.mc_base and self.world >= 8) else "ce_unicast"))
+        self._scheme_forced = forced is not None
+
+    def scheme_candidates(self):
+        c = ["ce_unicast", "sm_unicast:16", "sm_unicast:32"]
+        if self.mc_base:
+            c += ["ce_multicast", "sm_multicast:8", "sm_multicast:16", "sm_multicast:32", "sm_multicast:64"]
+        return c
+
+    def set_scheme(self, scheme):
+        kind, _, arg = scheme.partition(":")
+        if kind not in self.SCHEME_HOW or (kind.endswith("multicast") and not self.mc_base):
+            raise ValueError("unknown or unavailable pipeline scheme %r" % scheme)
+        self.scheme, self.scheme_kind, self.scheme_ctas = scheme, kind, int(arg or 0)
+
+    def tune_pipeline(self, stream, steps=6):
+        """Times `steps` pipelined steps (exchange drained inside) with every scheme this box offers, takes the MAX over
+        ranks and keeps the fastest.  Called during warm-up, outside any timed region; every rank ends up with the same
+        choice.  Also measures, for the chosen scheme, the SpMV alone and the exchange alone."""
+        import torch
+        import torch.distributed as dist
+
+        if self.exchange != "pipeline" or self.symm is None:
+            return None
+        res = {}
+        cands = [self.scheme] if self._scheme_forced else self.scheme_candidates()
+        for cand in cands:
+            self.set_scheme(cand)
+            for _ in range(2):
+                self.step(stream)
+            self.finish(stream)
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                self.step(stream)
+            self.finish(stream)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res[cand] = float(t[0])
+        best = min(res, key=res.get)
+        self.set_scheme(best)
+        # the two halves of a step, each alone (same MAX over ranks): what the overlap has to hide
+        parts = {}
+        for name, fn in (("spmv_alone_ms", lambda: self.A.mult_device(self.x, self.y_src[0], self.variant, stream)),
+                         ("exchange_alone_ms", lambda: self._push(0, stream, on_main=True))):
+            fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            parts[name] = float(t[0])
+        self.symm.barrier(channel=0)
+        torch.cuda.synchronize()
+        self.tuning = {"candidates_ms_per_step": res, "chosen": best, **parts}
+        return self.tuning
+
+    def _push(self, b, stream, on_main=False):
+        """Sends my rows of buffer b (y_src[b]) into every rank's y_sym[b], then a device-side barrier over all ranks on
+        the same stream: once copy_done[b] has passed, step k's y is complete on EVERY rank (per-step completion, not
+        just a drain at the end)."""
+        import torch
+
+        nbytes = 8 * (self.r1 - self.r0)
+        off = 8 * (b * self.M + self.r0)
+        src = self.y_src[b]
+        ps = stream if on_main else self.push_stream
+        if self.scheme_kind == "ce_unicast":
+            if on_main:
+                for pv in self.peer_views:
+                    pv[b * self.M + self.r0:b * self.M + self.r1].copy_(src, non_blocking=True)
+            else:
+                for pv, cs in zip(self.peer_views, self.ce_streams):
+                    cs.wait_event(self.spmv_done[b])
+                    with torch.cuda.stream(cs):
+                        pv[b * self.M + self.r0:b * self.M + self.r1].copy_(src, non_blocking=True)
+                    ps.wait_stream(cs)
+            # my own copy of my rows
+            with torch.cuda.stream(ps):
+                self.y_sym[b * self.M + self.r0:b * self.M + self.r1].copy_(src, non_blocking=True)
+        elif self.scheme_kind == "ce_multicast":
+            self.eng.copy_device(self.mc_base + off, src, nbytes, ps)
+        elif self.scheme_kind == "sm_multicast":
+            self.eng.push_device(self.mc_base + off, src, nbytes, self.scheme_ctas, ps)
+        else:  # sm_unicast: every peer's buffer and my own
+            dsts = [p + off for p in self.peer_ptrs] + [int(self.symm.buffer_ptrs[self.rank]) + off]
+            self.eng.push_fanout_device(dsts, src, nbytes, self.scheme_ctas, ps)
+        with torch.cuda.stream(ps):
+            self.symm.barrier(channel=1 + b)
+
+    @property
+    def partition_desc(self):
+        how = {"nccl": "all-gathered by ONE NCCL all_gather_into_tensor on equal padded slots + compaction",
+               "multicast": "stored by the SpMV kernel to the NVSwitch multicast address of y (fused, no collective) + device "
+               "barrier",
                "p2p": "stored by the SpMV kernel into every rank's y through NVLink peer mappings (fused, no collective) "
                "+ device barrier",
                "copy": "pushed to every rank by the copy engines over NVLink, sub-block by sub-block, while the next "
                "sub-block's SpMV runs (%d sub-blocks) + device barrier" % len(self.subs),
-               "pipeline": ("pushed to every rank by ONE %s per step to the NVSwitch multicast address "
-                            "(two y buffers): step k's exchange overlaps step k+1's SpMV, the pipe is drained inside the "
-                            "timed region" % ("small SM copy kernel (%d CTAs)" % self.push_ctas
-                                              if getattr(self, "push_ctas", 0) > 0 else "copy-engine transfer"))
-               if self.mc_base is not None else
-               ("pushed to every rank by the copy engines over NVLink (peer copies, two y buffers): step k's "
-                "exchange overlaps step k+1's SpMV, the pipe is drained inside the timed region"),
-               "none": "kept local"}[exchange if world > 1 else "none"]
-        self.partition_desc = "row blocks balanced by nnz, %d ranks; x replicated; y %s" % (world, how)
+               "pipeline": "pushed to every rank by %s, followed by a device barrier over all ranks (two y buffers): step k's "
+               "exchange overlaps step k+1's SpMV, a step's y is complete everywhere one step later, the pipe is drained "
+               "inside the timed region" % (
+                   (self.SCHEME_HOW[self.scheme_kind] % self.scheme_ctas if "%d" in self.SCHEME_HOW[self.scheme_kind]
+                    else self.SCHEME_HOW[self.scheme_kind]) if self.scheme else "?"),
+               "none": "kept local"}[self.exchange if self.world > 1 else "none"]
         self._exchange_how = how
-        self.x = None
-        self._source_desc = source.desc
+        return "row blocks balanced by nnz, %d ranks; x replicated; y %s" % (self.world, how)
 
     def set_x(self, x, stream=None):
         """The x of the following steps (constant over the reference's -n loop): smvp_csr_set_x_device on every
@@ -319,56 +469,64 @@ class RowBlockCsr:
             A.set_x_device(x, stream)
         self.x = None  # passes use the x declared above
 
+    def _timed_mult(self, A, y, main):
+        if self.spmv_events is not None:
+            self.spmv_events[0].record(main)
+        A.mult_device(self.x, y, self.variant, main)
+        if self.spmv_events is not None:
+            self.spmv_events[1].record(main)
+
     def multiply(self, stream=None):
         import torch
 
+        main = stream if stream is not None else torch.cuda.current_stream()
         if self.y_fan is not None:
+            if self.spmv_events is not None:
+                self.spmv_events[0].record(main)
             self.A.mult_device_fanout(self.x, self.y_fan, self.variant, stream)
-        elif self.mc_base is not None:
-            main = stream if stream is not None else torch.cuda.current_stream()
+            if self.spmv_events is not None:
+                self.spmv_events[1].record(main)
+        elif self.exchange == "pipeline" and self.symm is not None:
             b = self.k % self.nbuf
-            if self.copy_pending[b]:  # the copy that still reads this source buffer (two steps ago) must be done
-                main.wait_event(self.copy_done[b][0])
+            if self.copy_pending[b]:  # the push that still reads this source buffer (two steps ago) must be done
+                main.wait_event(self.copy_done[b])
             self.y_local = self.y_src[b]
             self.y_full = self.y_sym[b * self.M:(b + 1) * self.M]
-            self.A.mult_device(self.x, self.y_local, self.variant, main)
-            self.sub_events[b][0].record(main)
-            self.copy_stream.wait_event(self.sub_events[b][0])
-            if self.push_ctas > 0:
-                self.eng.push_device(self.mc_base + 8 * (b * self.M + self.r0), self.y_local, 8 * (self.r1 - self.r0),
-                                     self.push_ctas, self.copy_stream)
-            else:
-                self.eng.copy_device(self.mc_base + 8 * (b * self.M + self.r0), self.y_local, 8 * (self.r1 - self.r0),
-                                     self.copy_stream)
+            self._timed_mult(self.A, self.y_local, main)  # the event bracket opens AFTER the wait: SpMV time only
+            self.spmv_done[b].record(main)
+            self.push_stream.wait_event(self.spmv_done[b])
+            self._push(b, main)
         elif self.peer_views is not None:
-            main = stream if stream is not None else torch.cuda.current_stream()
-            b = self.k % self.nbuf
-            off = b * self.M
-            if self.copy_pending[b]:  # the copies that still read this buffer (two steps ago) must be done
-                for ev in self.copy_done[b]:
-                    main.wait_event(ev)
+            off = 0
             self.y_full = self.y_sym[off:off + self.M]
             self.y_local = self.y_full[self.r0:self.r1]
+            if self.spmv_events is not None:
+                self.spmv_events[0].record(main)
             for g, A in enumerate(self.subs):
                 a0, a1 = off + self.sub_bounds[g], off + self.sub_bounds[g + 1]
                 A.mult_device(self.x, self.y_sym[a0:a1], self.variant, main)
-                self.sub_events[b][g].record(main)
+                self.sub_events[0][g].record(main)
                 for pv, cs in zip(self.peer_views, self.copy_streams):
                     with torch.cuda.stream(cs):
-                        cs.wait_event(self.sub_events[b][g])
+                        cs.wait_event(self.sub_events[0][g])
                         pv[a0:a1].copy_(self.y_sym[a0:a1], non_blocking=True)
+            if self.spmv_events is not None:
+                self.spmv_events[1].record(main)
         else:
-            self.A.mult_device(self.x, self.y_write if self.y_write is not None else self.y_local, self.variant, stream)
+            self._timed_mult(self.A, self.y_write if self.y_write is not None else self.y_local, main)
 
     def exchange_y(self, stream=None):
         if self.world > 1 and self.exchange == "nccl":
             import torch.distributed as dist
 
-            allgather_v(dist, self.y_full, self.bounds, self.rank)
-        elif self.exchange == "pipeline":
+            if dist.get_backend() == "nccl":
+                allgather_padded(dist, self.y_pad, self.y_full, self.bounds, self.rank, self.per)
+            else:
+                self.y_full[self.r0:self.r1] = self.y_local
+                allgather_v(dist, self.y_full, self.bounds, self.rank)
+        elif self.exchange == "pipeline" and self.symm is not None:
             b = self.k % self.nbuf
-            for ev, cs in zip(self.copy_done[b], self.copy_streams):
-                ev.record(cs)
+            self.copy_done[b].record(self.push_stream)
             self.copy_pending[b] = True
             self.k += 1
         elif self.symm is not None:
@@ -386,9 +544,14 @@ class RowBlockCsr:
             import torch
 
             main = stream if stream is not None else torch.cuda.current_stream()
-            for cs in self.copy_streams:
-                main.wait_stream(cs)
-            self.symm.barrier(channel=0)
+            main.wait_stream(self.push_stream)
+
+    def last_y(self):
+        """The full y of the LAST completed step (after finish()), as this rank holds it."""
+        if self.exchange == "pipeline" and self.symm is not None:
+            b = (self.k - 1) % self.nbuf
+            return self.y_sym[b * self.M:(b + 1) * self.M]
+        return self.y_full
 
     def step(self, stream=None):
         self.multiply(stream)
@@ -403,6 +566,7 @@ class RowBlockCsr:
             return ("every rank: smvp_csr_mult(A_block, x_host, y_host_block, iters=1) [C ABI, pinned host buffers]; the "
                     "pipelined pass uploads only the window of x the row block reads and downloads the block's rows; "
                     "the host holds all of y, no device-side exchange of y on this path")
+        self.partition_desc
         return ("H2D of each rank's 1/N slice of x -> NCCL all-gather of x -> smvp_csr_mult_device -> %s -> D2H of "
                 "each rank's y block" % self._exchange_how)
 
@@ -473,7 +637,7 @@ class RowBlockCsr:
     def free(self):
         for A in self.subs:
             A.free()
-        self.y_full = self.y_local = self.peer_views = self.y_sym = self.y_src = None
+        self.y_full = self.y_local = self.peer_views = self.y_sym = self.y_src = self.y_pad = None
 
 
 class ColBlockTjds:
@@ -508,14 +672,23 @@ class ColBlockTjds:
         self.Mp = -(-self.M // world) * world
         self.y_partial = torch.zeros(self.Mp, dtype=torch.float64, device="cuda")
         self.y_owned = torch.zeros(self.Mp // world, dtype=torch.float64, device="cuda")
+        # deterministic variant: the N-way sum is done in rank order by our own kernel after an all-to-all of the blocks,
+        # so the bits do not depend on NCCL's reduction order (SMVP_TJDS_ORDERED=0/1 forces it off/on for either variant)
+        forced = os.environ.get("SMVP_TJDS_ORDERED")
+        self.ordered = world > 1 and exchange == "nccl" and (
+            forced == "1" or (forced != "0" and variant == eng.TJDS_DETERMINISTIC))
+        self.scratch = torch.empty(self.Mp, dtype=torch.float64, device="cuda") if self.ordered else None
         self.local_rows_out = self.Mp // world
         self.variant_name = {eng.TJDS_ATOMIC: "atomic", eng.TJDS_DETERMINISTIC: "deterministic"}[variant]
         self.kernel_name = "tjds_%s_kernel" % ("atomic" if variant == eng.TJDS_ATOMIC else "det")
         self.partition_desc = ("column blocks balanced by nnz, %d ranks; x sliced; partial y %s" %
-                               (world, "reduce-scattered over NCCL" if (world > 1 and exchange == "nccl") else "kept local"))
+                               (world, ("exchanged block-wise (NCCL all-to-all) and summed in rank order by "
+                                        "smvp_sum_ordered_device: reproducible run to run" if self.ordered else
+                                        "reduce-scattered over NCCL") if (world > 1 and exchange == "nccl") else "kept local"))
         self.e2e_api = ("smvp_tjds_mult(A, x_host, y_host, iters=1) [C ABI, pinned host buffers]" if world == 1 else
                         "H2D x slice -> smvp_tjds_set_x_device + smvp_tjds_mult_device -> NCCL reduce-scatter -> D2H y block")
         self.x = None
+        self.spmv_events = None
 
     def plan_desc(self):
         if self.T.y_relabel == 1:
@@ -528,16 +701,31 @@ class ColBlockTjds:
         self.T.set_x_device(x[self.c0:self.c1], stream)
 
     def multiply(self, stream=None):
-        self.T.mult_device(self.y_partial, self.variant, 0, stream)
+        if self.spmv_events is not None:
+            import torch
+
+            main = stream if stream is not None else torch.cuda.current_stream()
+            self.spmv_events[0].record(main)
+            self.T.mult_device(self.y_partial, self.variant, 0, stream)
+            self.spmv_events[1].record(main)
+        else:
+            self.T.mult_device(self.y_partial, self.variant, 0, stream)
 
     def exchange_y(self, stream=None):
         if self.world > 1 and self.exchange == "nccl":
             import torch.distributed as dist
 
-            reduce_scatter_sum(dist, self.y_owned, self.y_partial, self.rank)
+            if self.ordered:
+                reduce_scatter_ordered(dist, self.eng, self.y_owned, self.y_partial, self.scratch, self.rank, self.world, stream)
+            else:
+                reduce_scatter_sum(dist, self.y_owned, self.y_partial, self.rank)
 
     def finish(self, stream=None):
         pass
+
+    def last_y(self):
+        """This rank's block of y (rows [rank * Mp/world, ...)) after the exchange."""
+        return self.y_owned
 
     def step(self, stream=None):
         self.multiply(stream)
@@ -564,4 +752,4 @@ class ColBlockTjds:
 
     def free(self):
         self.T.free()
-        self.y_partial = self.y_owned = None
+        self.y_partial = self.y_owned = self.scratch = None

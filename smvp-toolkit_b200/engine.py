@@ -50,7 +50,8 @@ class _CsrInfo(ctypes.Structure):
 class _TjdsInfo(ctypes.Structure):
     _fields_ = [("rows", ctypes.c_int32), ("cols", ctypes.c_int32), ("nnz", ctypes.c_int64), ("ndiag", ctypes.c_int32),
                 ("ref_diag_limit", ctypes.c_int32), ("input_order", ctypes.c_int32), ("bytes_per_mult", ctypes.c_int64),
-                ("device_bytes", ctypes.c_int64), ("launches_per_mult", ctypes.c_int32 * 2), ("y_relabel", ctypes.c_int32)]
+                ("device_bytes", ctypes.c_int64), ("launches_per_mult", ctypes.c_int32 * 2), ("y_relabel", ctypes.c_int32),
+                ("skewed_walk", ctypes.c_int32), ("det_route", ctypes.c_int32)]
 
 
 class _TimeStats(ctypes.Structure):
@@ -97,6 +98,8 @@ SIGNATURES = {
     "smvp_vector_add_device": (_int, [_vp, _vp, _i64, _vp]),
     "smvp_copy_device": (_int, [_vp, _vp, _i64, _vp]),
     "smvp_push_device": (_int, [_vp, _vp, _i64, _int, _vp]),
+    "smvp_push_fanout_device": (_int, [_vp, _int, _vp, _i64, _int, _vp]),
+    "smvp_sum_ordered_device": (_int, [_vp, _vp, _int, _i64, _i64, _vp]),
     "smvp_flush_l2": (_int, [_i64, _vp]),
     "smvp_device_free": (None, [_vp]),
 }
@@ -306,6 +309,12 @@ class TjdsMatrix:
         _check(lib().smvp_tjds_info(self._h, ctypes.byref(info)), "smvp_tjds_info")
         return info.y_relabel
 
+    def plan(self):
+        """(skewed_walk, det_route) as smvp_tjds_info_t reports them now (see include/smvp_cuda.h)."""
+        info = _TjdsInfo()
+        _check(lib().smvp_tjds_info(self._h, ctypes.byref(info)), "smvp_tjds_info")
+        return info.skewed_walk, info.det_route
+
     @classmethod
     def build(cls, coo, rows, cols):
         """COO on the host -> TJDS in HBM (smvp_tjds_build; replaces main-cli.c:755-967)."""
@@ -439,6 +448,15 @@ def copy_device(d_dst, d_src, nbytes, stream=None):
 
 def push_device(d_dst, d_src, nbytes, ctas=16, stream=None):
     _check(lib().smvp_push_device(_ptr(d_dst), _ptr(d_src), nbytes, ctas, _stream(stream)), "smvp_push_device")
+
+
+def push_fanout_device(dst_ptrs, d_src, nbytes, ctas=16, stream=None):
+    arr = (ctypes.c_void_p * len(dst_ptrs))(*[int(p) for p in dst_ptrs])
+    _check(lib().smvp_push_fanout_device(arr, len(dst_ptrs), _ptr(d_src), nbytes, ctas, _stream(stream)), "smvp_push_fanout_device")
+
+
+def sum_ordered_device(d_out, d_parts, nparts, stride, n, stream=None):
+    _check(lib().smvp_sum_ordered_device(_ptr(d_out), _ptr(d_parts), nparts, stride, n, _stream(stream)), "smvp_sum_ordered_device")
 
 
 def flush_l2(nbytes=256 << 20, stream=None):

@@ -58,6 +58,13 @@ def _worker(rank, world, port, name, out):
         per = -(-m // world)
         lo, hi = rank * per, min((rank + 1) * per, m)
         err_tjds = float(np.linalg.norm(owned.numpy()[: hi - lo] - y_ref[lo:hi]) / np.linalg.norm(y_ref))
+        # the rank-ordered combine (what the deterministic variant uses at N > 1): same blocks, fixed summation order
+        owned2 = sdist.col_block_spmv(dist, lambda xs: torch.from_numpy(oracle.tjds_mult(t, xs.numpy())), cb, rank, world, x, m,
+                                      ordered=True)
+        owned3 = sdist.col_block_spmv(dist, lambda xs: torch.from_numpy(oracle.tjds_mult(t, xs.numpy())), cb, rank, world, x, m,
+                                      ordered=True)
+        assert torch.equal(owned2, owned3), "rank-ordered combine must be bit-identical run to run"
+        err_tjds = max(err_tjds, float(np.linalg.norm(owned2.numpy()[: hi - lo] - y_ref[lo:hi]) / np.linalg.norm(y_ref)))
         nnz_share = len(blk) / max(len(coo), 1)
         out[rank] = (err_csr, err_tjds, nnz_share, rb, cb)
     finally:
