@@ -9,7 +9,7 @@ PKG       := smvp-toolkit_b200
 LIB       := $(PKG)/lib
 OBJ       := $(LIB)/obj
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden
+NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -DSMVP_BUILDING_LIB
 CFLAGS    := -O2 -std=gnu11 -Wall -Wextra -D_XOPEN_SOURCE=700 -Iinclude -I$(PKG)/host
 
 CU_SRCS   := $(wildcard $(PKG)/csrc/*.cu)

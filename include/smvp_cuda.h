@@ -178,6 +178,12 @@ int smvp_csr_arrays_device(const smvp_csr *A, const int32_t **d_row_ptr, const i
 void smvp_csr_free(smvp_csr *A);
 void smvp_tjds_free(smvp_tjds *A);
 
+/* page-locked host memory for the x / y vectors of the host entry points (NULL on failure).  smvp_csr_mult overlaps
+ * its PCIe transfers with the multiply only when both vectors are page-locked; pageable buffers (malloc) are served by
+ * plain copies -- same result, no overlap. */
+void *smvp_host_alloc(int64_t bytes);
+void smvp_host_free(void *p);
+
 const char *smvp_strerror(int code);
 /* text of the last CUDA error seen by this thread's last failing call ("" if none) */
 const char *smvp_last_cuda_error(void);

@@ -67,6 +67,11 @@ int smvp_push_fanout_device(void *const *d_dst_list, int n_dst, const void *d_sr
  * partial results (column-block TJDS), bit-identical whatever order the parts arrived in */
 int smvp_sum_ordered_device(double *d_out, const double *d_parts, int nparts, int64_t stride, int64_t n, void *stream);
 
+/* the same with the parts given as nparts (<= 16) separate 16-byte-aligned device pointers (HOST array), e.g. the peer
+ * mappings of a symmetric-memory buffer: the owner of a row block pulls that block of every rank's partial y over
+ * NVLink and adds them in rank order */
+int smvp_sum_ordered_ptrs_device(double *d_out, const double *const *d_part_list, int nparts, int64_t n, void *stream);
+
 /* L2 flush helper for timing hygiene: writes `bytes` of a scratch buffer owned by the library */
 int smvp_flush_l2(int64_t bytes, void *stream);
 

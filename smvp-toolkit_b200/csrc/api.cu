@@ -38,6 +38,24 @@ extern "C" int smvp_device_count(void)
     return n;
 }
 
+// page-locked host buffers for x and y (plain C callers need no CUDA header): what makes the overlapped transfers of
+// smvp_csr_mult effective
+extern "C" void *smvp_host_alloc(int64_t bytes)
+{
+    void *p = nullptr;
+    if (bytes < 0 || cudaHostAlloc(&p, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void smvp_host_free(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
+}
+
 extern "C" int64_t smvp_launch_count(void) { return (int64_t)g_launches.load(); }
 
 namespace smvp

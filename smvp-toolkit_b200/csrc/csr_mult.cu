@@ -984,8 +984,21 @@ static int env_int(const char *name, int dflt, int lo, int hi)
     return v < lo ? lo : (v > hi ? hi : v);
 }
 // defaults from the sweep on B200 (tools/sweep_e2e.py, profiles/): tuning hooks SMVP_PIPE_RANGES / SMVP_PIPE_XCHUNKS
-static int pipe_ranges() { return env_int("SMVP_PIPE_RANGES", 32, 1, PIPE_MAX_RANGES); }
-static int pipe_xchunks() { return env_int("SMVP_PIPE_XCHUNKS", 64, 1, PIPE_MAX_XCHUNKS); }
+// The sweep found 32 ranges x 64 upload pieces best for a 402 MB vector: 12.6 MB per download piece, 6.3 MB per upload
+// piece, each piece costing ~23 us on its stream.  Smaller vectors (the row block of one GPU out of N) keep the PIECE
+// SIZE, not the piece count, so the fixed cost of a call shrinks with the block (round 1: e2e did not scale with N).
+constexpr int64_t PIPE_DOWN_PIECE_BYTES = 12 << 20;
+constexpr int64_t PIPE_UP_PIECE_BYTES = 6 << 20;
+static int pipe_ranges(int64_t y_bytes)
+{
+    const int64_t want = ceil_div64(y_bytes, PIPE_DOWN_PIECE_BYTES);
+    return env_int("SMVP_PIPE_RANGES", (int)(want < 2 ? 2 : (want > 32 ? 32 : want)), 1, PIPE_MAX_RANGES);
+}
+static int pipe_xchunks(int64_t x_bytes)
+{
+    const int64_t want = ceil_div64(x_bytes, PIPE_UP_PIECE_BYTES);
+    return env_int("SMVP_PIPE_XCHUNKS", (int)(want < 2 ? 2 : (want > 64 ? 64 : want)), 1, PIPE_MAX_XCHUNKS);
+}
 
 // largest and smallest column index among nonzeros [n0, n1): out[0] = max (start -1), out[1] = min (start INT32_MAX)
 __global__ void __launch_bounds__(256) col_range_kernel(const int32_t *__restrict__ col_ind, int64_t n0, int64_t n1,
@@ -1014,7 +1027,7 @@ __global__ void __launch_bounds__(256) col_range_kernel(const int32_t *__restric
 static int pipe_plan(smvp_csr *A)
 {
     SMVP_TRY(merge_plan(A, pick_merge_cfg(A), 0));
-    const int NR = pipe_ranges();
+    const int NR = pipe_ranges(8 * (int64_t)A->rows);
     if (A->pipe_cfg == A->merge_cfg && A->pipe_ranges == NR)
         return SMVP_OK;
     const int32_t T = A->merge_tiles;
@@ -1077,11 +1090,16 @@ static int pipe_streams() { return env_int("SMVP_PIPE_STREAMS", 1, 1, PIPE_MAX_S
 
 struct PipeResources
 {
-    cudaStream_t up[PIPE_MAX_STREAMS] = {}, down[PIPE_MAX_STREAMS] = {};
+    cudaStream_t up[PIPE_MAX_STREAMS] = {}, down[PIPE_MAX_STREAMS] = {}, compute = nullptr;
     cudaEvent_t x_ready[PIPE_MAX_XCHUNKS] = {}, done[PIPE_MAX_RANGES] = {}, t0[PIPE_MAX_RANGES] = {}, t1[PIPE_MAX_RANGES] = {};
+    cudaEvent_t begin = nullptr;
     cudaError_t create()
     {
-        cudaError_t e = cudaSuccess;
+        // the pass runs on its own non-blocking stream: the legacy stream would serialise it against every other
+        // blocking stream of the process
+        cudaError_t e = cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking);
+        if (e == cudaSuccess)
+            e = cudaEventCreateWithFlags(&begin, cudaEventDisableTiming);
         for (int k = 0; k < PIPE_MAX_STREAMS && e == cudaSuccess; k++)
         {
             e = cudaStreamCreateWithFlags(&up[k], cudaStreamNonBlocking);
@@ -1102,6 +1120,10 @@ struct PipeResources
     }
     ~PipeResources()
     {
+        if (begin)
+            cudaEventDestroy(begin);
+        if (compute)
+            cudaStreamDestroy(compute);
         for (int c = 0; c < PIPE_MAX_XCHUNKS; c++)
             if (x_ready[c])
                 cudaEventDestroy(x_ready[c]);
@@ -1152,57 +1174,77 @@ static int csr_mult_pipelined(smvp_csr *A, const double *x_host, double *y_host,
         A->pipe_res = fresh;
     }
     PipeResources &R = *static_cast<PipeResources *>(A->pipe_res);
-    const int NR = A->pipe_ranges, NX = pipe_xchunks(), NS = pipe_streams();
     // the part of x this matrix reads: [xlo, xhi).  Entries outside it are never gathered, so they are not uploaded
+    const int NR = A->pipe_ranges, NS = pipe_streams();
     const int64_t xlo = A->pipe_xlo, xhi = NR > 0 ? A->pipe_xneed[NR - 1] : 0;
     const int64_t xlen = xhi > xlo ? xhi - xlo : 0;
+    const int NX = pipe_xchunks(8 * xlen);
     const int64_t xchunk = ((ceil_div64(xlen > 0 ? xlen : 1, NX) + 63) / 64) * 64; // entries per upload piece (512 B multiple)
+    cudaStream_t cs = R.compute;
+    // first failing runtime call of the pass; later calls are skipped, the streams are still drained below
+#define PIPE_CK(expr)            \
+    do                           \
+    {                            \
+        if (e == cudaSuccess)    \
+            e = (expr);          \
+    } while (0)
+    // everything queued on the legacy stream before the call (the zero-fill of y, an earlier pass) comes first
+    PIPE_CK(cudaEventRecord(R.begin, 0));
+    PIPE_CK(cudaStreamWaitEvent(cs, R.begin, 0));
+    for (int k = 0; k < NS; k++)
+    {
+        PIPE_CK(cudaStreamWaitEvent(R.up[k], R.begin, 0));
+        PIPE_CK(cudaStreamWaitEvent(R.down[k], R.begin, 0));
+    }
     if (x_host)
     {
         for (int k = 0; k < NX; k++)
         {
             const int64_t a = xlo + (int64_t)k * xchunk, b = a + xchunk < xhi ? a + xchunk : xhi;
             if (b > a)
-                cudaMemcpyAsync(A->d_x + a, x_host + a, sizeof(double) * (size_t)(b - a), cudaMemcpyHostToDevice, R.up[k % NS]);
-            cudaEventRecord(R.x_ready[k], R.up[k % NS]);
+                PIPE_CK(cudaMemcpyAsync(A->d_x + a, x_host + a, sizeof(double) * (size_t)(b - a), cudaMemcpyHostToDevice, R.up[k % NS]));
+            PIPE_CK(cudaEventRecord(R.x_ready[k], R.up[k % NS]));
         }
     }
     int rc = SMVP_OK;
     const double *xm = A->relabel_state == 1 ? A->x_rel : A->d_x; // callers upload under the pass only without relabelling
     int waited = -1; // last upload piece the compute stream already waits for
-    for (int c = 0; c < NR && rc == SMVP_OK; c++)
+    for (int c = 0; c < NR && rc == SMVP_OK && e == cudaSuccess; c++)
     {
         if (x_host && A->pipe_xneed[c] > xlo)
         {
             int k = (int)(((int64_t)A->pipe_xneed[c] - 1 - xlo) / xchunk);
             k = k < NX ? k : NX - 1;
             for (; waited < k; waited++) // pieces alternate over NS streams: wait for each one up to k
-                cudaStreamWaitEvent(0, R.x_ready[waited + 1], 0);
+                PIPE_CK(cudaStreamWaitEvent(cs, R.x_ready[waited + 1], 0));
         }
-        cudaEventRecord(R.t0[c], 0);
-        if (A->pipe_tile[c + 1] > A->pipe_tile[c])
-            rc = csr_mult_merge(A, xm, A->d_y, nullptr, 0, A->pipe_tile[c], A->pipe_tile[c + 1]);
-        cudaEventRecord(R.t1[c], 0);
+        PIPE_CK(cudaEventRecord(R.t0[c], cs));
+        if (A->pipe_tile[c + 1] > A->pipe_tile[c] && e == cudaSuccess)
+            rc = csr_mult_merge(A, xm, A->d_y, nullptr, cs, A->pipe_tile[c], A->pipe_tile[c + 1]);
+        PIPE_CK(cudaEventRecord(R.t1[c], cs));
         if (y_host)
         {
-            cudaEventRecord(R.done[c], 0);
-            cudaStreamWaitEvent(R.down[c % NS], R.done[c], 0);
+            PIPE_CK(cudaEventRecord(R.done[c], cs));
+            PIPE_CK(cudaStreamWaitEvent(R.down[c % NS], R.done[c], 0));
             const int32_t r0 = A->pipe_row[c], r1 = A->pipe_row[c + 1];
             if (r1 > r0)
-                cudaMemcpyAsync(y_host + r0, A->d_y + r0, sizeof(double) * (size_t)(r1 - r0), cudaMemcpyDeviceToHost,
-                                R.down[c % NS]);
+                PIPE_CK(cudaMemcpyAsync(y_host + r0, A->d_y + r0, sizeof(double) * (size_t)(r1 - r0), cudaMemcpyDeviceToHost,
+                                        R.down[c % NS]));
         }
     }
-    e = cudaStreamSynchronize(0);
+    // drain every stream of the pass, also after a failure (nothing may still touch the caller's buffers on return)
+    cudaError_t es = cudaStreamSynchronize(cs);
     for (int k = 0; k < NS; k++) // the upload streams too: a matrix may read less than all of x
     {
-        if (e == cudaSuccess)
-            e = cudaStreamSynchronize(R.up[k]);
-        if (e == cudaSuccess)
-            e = cudaStreamSynchronize(R.down[k]);
+        const cudaError_t eu = cudaStreamSynchronize(R.up[k]), ed = cudaStreamSynchronize(R.down[k]);
+        if (es == cudaSuccess)
+            es = eu != cudaSuccess ? eu : ed;
     }
+#undef PIPE_CK
     if (rc != SMVP_OK)
         return rc;
+    if (e == cudaSuccess)
+        e = es;
     if (e != cudaSuccess)
         return cuda_fail(e, "pipelined pass", __FILE__, __LINE__);
     float total = 0.f;
@@ -1228,8 +1270,22 @@ extern "C" int smvp_csr_mult(smvp_csr *A, const double *x_host, double *y_host, 
     if (!A->d_y)
         SMVP_CUDA(dev_alloc(&A->d_y, A->rows));
     const bool merge = csr_resolve_variant(A, variant) == SMVP_CSR_MERGE && A->rows > 0;
-    // big vectors: pipeline their PCIe transfers with the first / last pass (SMVP_NO_OVERLAP=1: plain copies)
-    const bool pipelined = merge && ((int64_t)A->rows + A->cols) >= (1 << 21) && getenv("SMVP_NO_OVERLAP") == nullptr;
+    // big vectors: pipeline their PCIe transfers with the first / last pass (SMVP_NO_OVERLAP=1: plain copies).
+    // Only from page-locked buffers (smvp_host_alloc, cudaHostAlloc, torch pin_memory): an asynchronous copy from or to
+    // PAGEABLE memory blocks the host until it is done, so every range would be enqueued only after the previous
+    // range's download and the GPU would idle in between -- plain copies are faster then.  SMVP_FORCE_OVERLAP=1
+    // pipelines regardless (tests).
+    auto page_locked = [](const void *p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return false;
+        }
+        return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+    };
+    const bool pipelined = merge && ((int64_t)A->rows + A->cols) >= (1 << 21) && getenv("SMVP_NO_OVERLAP") == nullptr &&
+                           (getenv("SMVP_FORCE_OVERLAP") != nullptr || (page_locked(x_host) && page_locked(y_host)));
     int rc = SMVP_OK;
     // plans outside the timed bracket (the reference builds its format before the loop too)
     if (A->rows > 0)

@@ -233,6 +233,44 @@ __global__ void __launch_bounds__(256) sum_ordered_kernel(double *__restrict__ o
     }
 }
 
+// the same with the parts given as separate pointers (peer mappings of a symmetric-memory buffer): the owner of a row
+// block PULLS that block of every rank's partial y over NVLink and adds them in rank order -- a reduce-scatter whose
+// bits do not depend on any library's reduction order
+struct PartPtrs
+{
+    const double *p[16];
+    int n;
+};
+__global__ void __launch_bounds__(256) sum_ordered_ptrs_kernel(double *__restrict__ out, const __grid_constant__ PartPtrs parts, int64_t n)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n2 = n / 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride)
+    {
+        double2 v[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) // all loads first: one NVLink round trip per element pair, not one per part
+            if (k < parts.n)
+                v[k] = reinterpret_cast<const double2 *>(parts.p[k])[i];
+        double2 acc = v[0];
+#pragma unroll
+        for (int k = 1; k < 16; k++)
+            if (k < parts.n)
+            {
+                acc.x = __dadd_rn(acc.x, v[k].x);
+                acc.y = __dadd_rn(acc.y, v[k].y);
+            }
+        reinterpret_cast<double2 *>(out)[i] = acc;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        double acc = parts.p[0][n - 1];
+        for (int k = 1; k < parts.n; k++)
+            acc = __dadd_rn(acc, parts.p[k][n - 1]);
+        out[n - 1] = acc;
+    }
+}
+
 static inline unsigned grid_for(int64_t n, int per_thread = 4)
 {
     int64_t blocks = ceil_div64(n > 0 ? n : 1, 256 * per_thread);
@@ -497,6 +535,28 @@ extern "C" int smvp_sum_ordered_device(double *d_out, const double *d_parts, int
     if (n > 0)
     {
         SMVP_LAUNCH(sum_ordered_kernel, grid_for(n), 256, 0, (cudaStream_t)stream, d_out, d_parts, nparts, stride, n);
+        SMVP_CUDA(cudaGetLastError());
+    }
+    return SMVP_OK;
+}
+
+extern "C" int smvp_sum_ordered_ptrs_device(double *d_out, const double *const *d_part_list, int nparts, int64_t n, void *stream)
+{
+    if (n < 0 || nparts < 1 || nparts > 16 || !d_part_list || (n > 0 && !d_out))
+        return SMVP_E_ARG;
+    PartPtrs parts;
+    parts.n = nparts;
+    for (int k = 0; k < 16; k++)
+    {
+        parts.p[k] = k < nparts ? d_part_list[k] : nullptr;
+        if (k < nparts && n > 0 && (!parts.p[k] || (((uintptr_t)parts.p[k]) & 15)))
+            return SMVP_E_ARG; // 16-byte aligned parts (128-bit loads)
+    }
+    if (n > 0 && (((uintptr_t)d_out) & 15))
+        return SMVP_E_ARG;
+    if (n > 0)
+    {
+        SMVP_LAUNCH(sum_ordered_ptrs_kernel, grid_for(n, 2), 256, 0, (cudaStream_t)stream, d_out, parts, n);
         SMVP_CUDA(cudaGetLastError());
     }
     return SMVP_OK;

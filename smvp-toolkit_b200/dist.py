@@ -391,7 +391,7 @@ class RowBlockCsr:
         self.set_scheme(best)
         # the two halves of a step, each alone (same MAX over ranks): what the overlap has to hide
         parts = {}
-        for name, fn in (("spmv_alone_ms", lambda: self.A.mult_device(self.x, self.y_src[0], self.variant, stream)),
+        for name, fn in (("spmv_alone_ms", lambda: self.A.mult_device(self.x, self._src(0), self.variant, stream)),
                          ("exchange_alone_ms", lambda: self._push(0, stream, on_main=True))):
             fn()
             torch.cuda.synchronize()
@@ -410,6 +410,14 @@ class RowBlockCsr:
         self.tuning = {"candidates_ms_per_step": res, "chosen": best, **parts}
         return self.tuning
 
+    def _src(self, b):
+        """Where the SpMV of buffer b writes my rows, and what the push reads.  Unicast schemes: straight into my own copy
+        of y (my rows need no transfer to myself).  Multicast schemes: a private staging buffer -- the switch writes my
+        rows into EVERY rank's y, mine included, and must not race with the kernel that produces them."""
+        if self.scheme_kind.endswith("multicast"):
+            return self.y_src[b]
+        return self.y_sym[b * self.M + self.r0:b * self.M + self.r1]
+
     def _push(self, b, stream, on_main=False):
         """Sends my rows of buffer b (y_src[b]) into every rank's y_sym[b], then a device-side barrier over all ranks on
         the same stream: once copy_done[b] has passed, step k's y is complete on EVERY rank (per-step completion, not
@@ -418,7 +426,7 @@ class RowBlockCsr:
 
         nbytes = 8 * (self.r1 - self.r0)
         off = 8 * (b * self.M + self.r0)
-        src = self.y_src[b]
+        src = self._src(b)
         ps = stream if on_main else self.push_stream
         if self.scheme_kind == "ce_unicast":
             if on_main:
@@ -430,16 +438,12 @@ class RowBlockCsr:
                     with torch.cuda.stream(cs):
                         pv[b * self.M + self.r0:b * self.M + self.r1].copy_(src, non_blocking=True)
                     ps.wait_stream(cs)
-            # my own copy of my rows
-            with torch.cuda.stream(ps):
-                self.y_sym[b * self.M + self.r0:b * self.M + self.r1].copy_(src, non_blocking=True)
         elif self.scheme_kind == "ce_multicast":
             self.eng.copy_device(self.mc_base + off, src, nbytes, ps)
         elif self.scheme_kind == "sm_multicast":
             self.eng.push_device(self.mc_base + off, src, nbytes, self.scheme_ctas, ps)
-        else:  # sm_unicast: every peer's buffer and my own
-            dsts = [p + off for p in self.peer_ptrs] + [int(self.symm.buffer_ptrs[self.rank]) + off]
-            self.eng.push_fanout_device(dsts, src, nbytes, self.scheme_ctas, ps)
+        else:  # sm_unicast: one kernel reads my rows once and stores them into every peer's buffer
+            self.eng.push_fanout_device([p + off for p in self.peer_ptrs], src, nbytes, self.scheme_ctas, ps)
         with torch.cuda.stream(ps):
             self.symm.barrier(channel=1 + b)
 
@@ -490,7 +494,7 @@ class RowBlockCsr:
             b = self.k % self.nbuf
             if self.copy_pending[b]:  # the push that still reads this source buffer (two steps ago) must be done
                 main.wait_event(self.copy_done[b])
-            self.y_local = self.y_src[b]
+            self.y_local = self._src(b)
             self.y_full = self.y_sym[b * self.M:(b + 1) * self.M]
             self._timed_mult(self.A, self.y_local, main)  # the event bracket opens AFTER the wait: SpMV time only
             self.spmv_done[b].record(main)
@@ -669,7 +673,7 @@ class ColBlockTjds:
         self.ndiag = nd
         self.global_bytes_per_mult = 12 * source.nnz + 4 * (nd + 1) + 8 * self.N + 8 * self.M
         self.local_bytes_per_mult = self.T.bytes_per_mult
-        self.Mp = -(-self.M // world) * world
+        self.Mp = -(-self.M // (2 * world)) * 2 * world  # blocks of an even number of rows: 16-byte aligned for 128-bit loads
         self.y_partial = torch.zeros(self.Mp, dtype=torch.float64, device="cuda")
         self.y_owned = torch.zeros(self.Mp // world, dtype=torch.float64, device="cuda")
         # deterministic variant: the N-way sum is done in rank order by our own kernel after an all-to-all of the blocks,
@@ -677,13 +681,33 @@ class ColBlockTjds:
         forced = os.environ.get("SMVP_TJDS_ORDERED")
         self.ordered = world > 1 and exchange == "nccl" and (
             forced == "1" or (forced != "0" and variant == eng.TJDS_DETERMINISTIC))
-        self.scratch = torch.empty(self.Mp, dtype=torch.float64, device="cuda") if self.ordered else None
+        self.scratch, self.symm, self.part_ptrs = None, None, None
+        if self.ordered:
+            # the partial y lives in symmetric memory: the owner of a row block pulls that block from every rank over
+            # NVLink and adds in rank order (smvp_sum_ordered_ptrs_device), between two device-side barriers.
+            # SMVP_TJDS_ORDERED_PULL=0: all-to-all of the blocks (NCCL) + local ordered sum instead.
+            if os.environ.get("SMVP_TJDS_ORDERED_PULL", "1") != "0":
+                try:
+                    import torch.distributed as dist
+                    import torch.distributed._symmetric_memory as symm_mem
+
+                    buf = symm_mem.empty(self.Mp, dtype=torch.float64, device=torch.device("cuda", torch.cuda.current_device()))
+                    buf.zero_()
+                    self.symm = symm_mem.rendezvous(buf, dist.group.WORLD.group_name)
+                    self.y_partial = buf
+                    per = self.Mp // world
+                    self.part_ptrs = [int(self.symm.buffer_ptrs[k]) + 8 * per * rank for k in range(world)]
+                except Exception:  # noqa: BLE001  (no peer access on this box)
+                    self.symm = None
+            if self.symm is None:
+                self.scratch = torch.empty(self.Mp, dtype=torch.float64, device="cuda")
         self.local_rows_out = self.Mp // world
         self.variant_name = {eng.TJDS_ATOMIC: "atomic", eng.TJDS_DETERMINISTIC: "deterministic"}[variant]
         self.kernel_name = "tjds_%s_kernel" % ("atomic" if variant == eng.TJDS_ATOMIC else "det")
         self.partition_desc = ("column blocks balanced by nnz, %d ranks; x sliced; partial y %s" %
-                               (world, ("exchanged block-wise (NCCL all-to-all) and summed in rank order by "
-                                        "smvp_sum_ordered_device: reproducible run to run" if self.ordered else
+                               (world, (("pulled block-wise over NVLink peer mappings" if self.symm is not None else
+                                         "exchanged block-wise (NCCL all-to-all)") + " and summed in rank order by our own "
+                                        "kernel: reproducible run to run" if self.ordered else
                                         "reduce-scattered over NCCL") if (world > 1 and exchange == "nccl") else "kept local"))
         self.e2e_api = ("smvp_tjds_mult(A, x_host, y_host, iters=1) [C ABI, pinned host buffers]" if world == 1 else
                         "H2D x slice -> smvp_tjds_set_x_device + smvp_tjds_mult_device -> NCCL reduce-scatter -> D2H y block")
@@ -715,7 +739,11 @@ class ColBlockTjds:
         if self.world > 1 and self.exchange == "nccl":
             import torch.distributed as dist
 
-            if self.ordered:
+            if self.ordered and self.symm is not None:
+                self.symm.barrier(channel=0)  # every rank's partial y is complete
+                self.eng.sum_ordered_ptrs_device(self.y_owned, self.part_ptrs, self.Mp // self.world, stream)
+                self.symm.barrier(channel=1)  # nobody refills its partial y while a peer still reads it
+            elif self.ordered:
                 reduce_scatter_ordered(dist, self.eng, self.y_owned, self.y_partial, self.scratch, self.rank, self.world, stream)
             else:
                 reduce_scatter_sum(dist, self.y_owned, self.y_partial, self.rank)
@@ -724,8 +752,10 @@ class ColBlockTjds:
         pass
 
     def last_y(self):
-        """This rank's block of y (rows [rank * Mp/world, ...)) after the exchange."""
-        return self.y_owned
+        """This rank's block of y (rows [rank * Mp/world, ...)) after the exchange; without an exchange the partial y."""
+        if self.world > 1 and self.exchange == "nccl":
+            return self.y_owned
+        return self.y_partial
 
     def step(self, stream=None):
         self.multiply(stream)

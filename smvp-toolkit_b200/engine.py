@@ -84,6 +84,8 @@ SIGNATURES = {
     "smvp_csr_arrays_device": (_int, [_vp, _pp, _pp, _pp]),
     "smvp_csr_free": (None, [_vp]),
     "smvp_tjds_free": (None, [_vp]),
+    "smvp_host_alloc": (_vp, [_i64]),
+    "smvp_host_free": (None, [_vp]),
     "smvp_strerror": (ctypes.c_char_p, [_int]),
     "smvp_last_cuda_error": (ctypes.c_char_p, []),
     "smvp_device_count": (_int, []),
@@ -100,6 +102,7 @@ SIGNATURES = {
     "smvp_push_device": (_int, [_vp, _vp, _i64, _int, _vp]),
     "smvp_push_fanout_device": (_int, [_vp, _int, _vp, _i64, _int, _vp]),
     "smvp_sum_ordered_device": (_int, [_vp, _vp, _int, _i64, _i64, _vp]),
+    "smvp_sum_ordered_ptrs_device": (_int, [_vp, _vp, _int, _i64, _vp]),
     "smvp_flush_l2": (_int, [_i64, _vp]),
     "smvp_device_free": (None, [_vp]),
 }
@@ -457,6 +460,11 @@ def push_fanout_device(dst_ptrs, d_src, nbytes, ctas=16, stream=None):
 
 def sum_ordered_device(d_out, d_parts, nparts, stride, n, stream=None):
     _check(lib().smvp_sum_ordered_device(_ptr(d_out), _ptr(d_parts), nparts, stride, n, _stream(stream)), "smvp_sum_ordered_device")
+
+
+def sum_ordered_ptrs_device(d_out, part_ptrs, n, stream=None):
+    arr = (ctypes.c_void_p * len(part_ptrs))(*[int(p) for p in part_ptrs])
+    _check(lib().smvp_sum_ordered_ptrs_device(_ptr(d_out), arr, len(part_ptrs), n, _stream(stream)), "smvp_sum_ordered_ptrs_device")
 
 
 def flush_l2(nbytes=256 << 20, stream=None):

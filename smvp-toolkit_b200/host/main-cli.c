@@ -111,6 +111,7 @@ int main(int argc, char *argv[])
     MM_typecode matcode;
     smvp_coo *coo = NULL;
     double *x, *y, *ms;
+    int pinned = 1;
     smvp_time_stats_t st;
     char path[4096];
 
@@ -211,8 +212,17 @@ int main(int argc, char *argv[])
     printf(ANSI_COLOR_CYAN "[DATA]\tNon-zero numbers contained in matrix: " ANSI_COLOR_RESET "%lld\n", (long long)nnz);
     printf(ANSI_COLOR_CYAN "[DATA]\tVector operand in use: " ANSI_COLOR_RESET "Ones vector with dimensions [%d, %d]\n", cols, 1);
 
-    x = (double *)malloc(sizeof(double) * (size_t)(cols > 0 ? cols : 1));
-    y = (double *)malloc(sizeof(double) * (size_t)(rows > 0 ? rows : 1));
+    /* page-locked: smvp_csr_mult overlaps the transfers of big vectors with the multiply only from such buffers */
+    x = (double *)smvp_host_alloc((int64_t)sizeof(double) * (cols > 0 ? cols : 1));
+    y = (double *)smvp_host_alloc((int64_t)sizeof(double) * (rows > 0 ? rows : 1));
+    if (!x || !y) /* no device / no page-locked memory: pageable buffers, the engine reports what is wrong */
+    {
+        smvp_host_free(x);
+        smvp_host_free(y);
+        pinned = 0;
+        x = (double *)malloc(sizeof(double) * (size_t)(cols > 0 ? cols : 1));
+        y = (double *)malloc(sizeof(double) * (size_t)(rows > 0 ? rows : 1));
+    }
     ms = (double *)malloc(sizeof(double) * (size_t)calc_iter);
     if (!x || !y || !ms)
         die("Out of memory.");
@@ -298,8 +308,16 @@ int main(int argc, char *argv[])
 
     printf(ANSI_COLOR_GREEN "[STOP]\tExit smvp-toolbox v%d.%d.%d\n\n" ANSI_COLOR_RESET, SMVP_MAJOR_VER, SMVP_MINOR_VER,
            SMVP_REVISION_VER);
-    free(x);
-    free(y);
+    if (pinned)
+    {
+        smvp_host_free(x);
+        smvp_host_free(y);
+    }
+    else
+    {
+        free(x);
+        free(y);
+    }
     free(ms);
     free(coo);
     return 0;

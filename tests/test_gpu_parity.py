@@ -297,6 +297,7 @@ def test_host_call_pipelined_transfers(eng, monkeypatch, banded):
 
     import torch
 
+    monkeypatch.setenv("SMVP_FORCE_OVERLAP", "1")  # numpy buffers are pageable: pipeline them anyway (slow but same path)
     m = n = (1 << 20) + 12345
     r = np.arange(m, dtype=np.int64)
     rows = [r, r[1:], r[:-1], r[3000:], r[:-3000]]
@@ -323,6 +324,10 @@ def test_host_call_pipelined_transfers(eng, monkeypatch, banded):
     rc = eng.lib().smvp_csr_mult(A._h, ctypes.c_void_p(hx.data_ptr()), ctypes.c_void_p(hy.data_ptr()), 1, None, eng.CSR_MERGE)
     assert rc == 0
     y_pinned = hy.numpy().copy()
+    # pageable buffers without the force switch: served by plain copies, same bits
+    monkeypatch.delenv("SMVP_FORCE_OVERLAP")
+    y_pageable, _ = A.mult(x, iters=2, variant=eng.CSR_MERGE)
+    assert np.array_equal(y_pageable.view(np.int64), outs[0].view(np.int64))
     monkeypatch.setenv("SMVP_NO_OVERLAP", "1")
     y_plain, _ = A.mult(x, iters=1, variant=eng.CSR_MERGE)
     y2_plain, _ = A.mult(x2, iters=1, variant=eng.CSR_MERGE)
@@ -332,11 +337,12 @@ def test_host_call_pipelined_transfers(eng, monkeypatch, banded):
     A.free()
 
 
-def test_host_call_pipelined_degenerate_shapes(eng):
+def test_host_call_pipelined_degenerate_shapes(eng, monkeypatch):
     """Shapes on which the pipelined host pass has little to pipeline: a tall matrix with 3 columns (x is one upload
     piece), a wide one with 4 rows (one tile range holds everything, the others are empty), a big matrix without a
     single nonzero (no range reads x), one whose FIRST row already reads the last column (every range waits
     for all of x), and one that reads only a window in the middle of x (the upload starts at the smallest column)."""
+    monkeypatch.setenv("SMVP_FORCE_OVERLAP", "1")
     rng = np.random.default_rng(41)
     big = (1 << 21) + 777
     cases = []

@@ -43,20 +43,36 @@ def main():
                         print("SKIP csr %s: %s" % (exch, e), flush=True)
                     break
                 op.set_x(x)
-                for _ in range(3):
-                    op.y_full.fill_(float("nan")) if exch == "nccl" else None
+                # the pipelined push: every scheme this box offers (copy engines / SM kernel, unicast / multicast)
+                schemes = op.scheme_candidates() if (exch == "pipeline" and variant == eng.CSR_MERGE) else [op.scheme]
+                for scheme in schemes:
+                    if scheme:
+                        op.set_scheme(scheme)
+                    for _ in range(3):
+                        op.y_full.fill_(float("nan")) if exch == "nccl" else None
+                        op.step(stream)
+                    op.finish(stream)
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    err = float(torch.linalg.norm(op.last_y() - y_ref)) / nrm
+                    ok = err <= 1e-12
+                    fails += 0 if ok else 1
+                    print("rank %d %-7s csr %-9s %-16s variant %d rows [%d,%d) x_relabel %d: rel_l2 %.2e %s" % (
+                        rank, kind, exch, scheme or "", variant, op.r0, op.r1, op.A.x_relabel, err, "ok" if ok else "FAIL"),
+                        flush=True)
+                if exch == "pipeline" and variant == eng.CSR_MERGE:
+                    tuned = op.tune_pipeline(stream, steps=3)
                     op.step(stream)
-                op.finish(stream)
-                torch.cuda.synchronize()
-                dist.barrier()
-                err = float(torch.linalg.norm(op.y_full - y_ref)) / nrm
-                ok = err <= 1e-12
-                fails += 0 if ok else 1
-                print("rank %d %-7s csr %-9s variant %d rows [%d,%d) x_relabel %d: rel_l2 %.2e %s" % (
-                    rank, kind, exch, variant, op.r0, op.r1, op.A.x_relabel, err, "ok" if ok else "FAIL"), flush=True)
+                    op.finish(stream)
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    err = float(torch.linalg.norm(op.last_y() - y_ref)) / nrm
+                    fails += 0 if err <= 1e-12 else 1
+                    if rank == 0:
+                        print("tuned pipeline: %s -> rel_l2 %.2e" % (tuned, err), flush=True)
                 op.free()
                 del op
-        if kind == "stencil":
+        if True:
             for variant in (eng.TJDS_ATOMIC, eng.TJDS_DETERMINISTIC):
                 op = sdist.ColBlockTjds(eng, src, rank, world, variant, exchange="nccl")
                 op.set_x(x, stream)
@@ -66,9 +82,18 @@ def main():
                 hi = min(lo + op.Mp // world, M)
                 err = float(torch.linalg.norm(op.y_owned[: hi - lo] - y_ref[lo:hi])) / nrm
                 ok = err <= 1e-12
+                tag = ""
+                if variant == eng.TJDS_DETERMINISTIC:
+                    # reproducible run to run INCLUDING the exchange: the N-way sum is taken in rank order
+                    keep = op.y_owned.clone()
+                    for _ in range(3):
+                        op.step(stream)
+                        torch.cuda.synchronize()
+                        ok = ok and bool(torch.equal(op.y_owned, keep))
+                    tag = " ordered=%s run-to-run %s" % (op.ordered, "bit-identical" if ok else "DIFFERS")
                 fails += 0 if ok else 1
-                print("rank %d %-7s tjds nccl     variant %d cols [%d,%d): rel_l2 %.2e %s" % (
-                    rank, kind, variant, op.c0, op.c1, err, "ok" if ok else "FAIL"), flush=True)
+                print("rank %d %-7s tjds nccl     variant %d cols [%d,%d): rel_l2 %.2e %s%s" % (
+                    rank, kind, variant, op.c0, op.c1, err, "ok" if ok else "FAIL", tag), flush=True)
                 op.free()
         whole.free()
     t = torch.tensor([fails], device="cuda")
