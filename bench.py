@@ -115,7 +115,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.01)
 
     def result(self):
         if not self.ok or not self.samples:
@@ -296,7 +296,10 @@ def timed_steps(ctx, op, steps, warmup, sample_clocks=True):
         op.step(stream)
     op.finish(stream)
     ctx.barrier()
-    sampler = ClockSampler(ctx.local_rank) if sample_clocks else None
+    # N > 1: only rank 0 polls NVML (its GPU's clocks are the ones reported).  A poll takes milliseconds inside the driver;
+    # with every rank polling, each one's hiccup reaches all ranks through the per-step barrier of the exchange
+    # (measured at 8 GPUs, tools/probe_steps.py: 0.628 ms per step without the pollers, 0.65 - 0.72 ms with 8 of them)
+    sampler = ClockSampler(ctx.local_rank) if (sample_clocks and ctx.rank == 0) else None
     launches0 = ctx.eng.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

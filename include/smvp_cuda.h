@@ -115,6 +115,11 @@ int smvp_csr_set_x_device(smvp_csr *A, const double *d_x, void *stream);
 /* one pass y = A x.  d_x == NULL: the x last given to smvp_csr_set_x_device.  d_x != NULL is always
  * correct too; on a relabelled handle it costs one extra permutation pass over x per call.             */
 int smvp_csr_mult_device(smvp_csr *A, const double *d_x, double *d_y, int variant, void *stream);
+/* The merge-path kernel runs as a persistent grid that fills every SM; `ctas_per_sm` > 0 makes it leave room for that
+ * many CTAs of ANOTHER kernel per SM (default 0).  A caller that runs a small kernel beside the multiply -- the
+ * multi-GPU path pushes the previous pass's rows to its peers while the next pass multiplies -- sets 1: without the
+ * room part of the persistent grid starts only when the co-runner retires and the pass ends that much later. */
+int smvp_csr_set_corunner_headroom(smvp_csr *A, int ctas_per_sm);
 /* one pass y = A x with the result stored into n_out (<= 8) destinations at once: d_y_list[k][r] = y[r] for
  * every row r of A and every k.  The destinations may be peer-mapped buffers of other GPUs (NVLink symmetric
  * memory): this is how the row-partitioned multi-GPU path fuses the "allgather of y" into the SpMV epilogue.

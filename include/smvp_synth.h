@@ -63,6 +63,11 @@ int smvp_push_device(void *d_dst, const void *d_src, int64_t bytes, int ctas, vo
  * all-gather of one rank's block of y into its peers' buffers).  d_dst_list is a HOST array of device pointers. */
 int smvp_push_fanout_device(void *const *d_dst_list, int n_dst, const void *d_src, int64_t bytes, int ctas, void *stream);
 
+/* the same fan-out issued through the TMA engine: `ctas` one-warp CTAs stream 16 KB chunks of the source through shared
+ * memory with cp.async.bulk and send every chunk to each destination with bulk stores -- full-size write packets, the
+ * source read once, almost no SM time.  Falls back to smvp_push_fanout_device for mutually misaligned pointers. */
+int smvp_push_tma_device(void *const *d_dst_list, int n_dst, const void *d_src, int64_t bytes, int ctas, void *stream);
+
 /* out[i] = (((p_0[i] + p_1[i]) + p_2[i]) + ...) with p_k = d_parts + k * stride: the fixed-order combine of per-rank
  * partial results (column-block TJDS), bit-identical whatever order the parts arrived in */
 int smvp_sum_ordered_device(double *d_out, const double *d_parts, int nparts, int64_t stride, int64_t n, void *stream);

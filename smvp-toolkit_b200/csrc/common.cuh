@@ -151,6 +151,7 @@ struct smvp_csr
     int32_t auto_variant;
     int64_t device_bytes;
     // merge-path plan (csr_mult.cu), built lazily
+    int32_t merge_headroom; // CTAs per SM the persistent merge-path grid leaves free for a co-running kernel (default 0)
     int32_t merge_cfg;      // which template instantiation the plan was made for (-1 none)
     int32_t merge_tiles;
     int32_t *tile_row;      // [merge_tiles+1] rows consumed before each tile

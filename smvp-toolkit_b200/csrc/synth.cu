@@ -219,6 +219,81 @@ __global__ void __launch_bounds__(512) push_fanout_kernel(const __grid_constant_
             fan.dst_tail[k][threadIdx.x] = src_tail[threadIdx.x];
 }
 
+// ---- the same fan-out done by the TMA engine: a CTA is ONE warp whose lane 0 streams 4 KB chunks of the source through a
+// ring of shared-memory stages with cp.async.bulk (global -> shared, mbarrier completion) and sends each stage to every
+// destination with cp.async.bulk (shared -> global, bulk groups).  No register staging, no per-thread stores: the SM
+// only issues descriptors, the copies leave the chip as full-size write packets (what a copy engine emits) and the
+// source is read once whatever the number of destinations.  `ctas` one-warp CTAs with 16 KB of shared memory each sit
+// beside the SpMV's CTAs; 64 of them keep ~1 MB in flight.
+// 4 x 4 KB = 16 KB per CTA, 6 registers: such a CTA fits into what a fully resident merge-path SpMV leaves free on an SM
+// (9 CTAs x (21.5 + 1) KB of the 228 KB of shared memory, 63 K of the 64 K registers), so the SpMV's persistent grid stays
+// completely resident beside it.  A co-runner that does NOT fit (the 512-thread store kernels above, or 64 KB stages here) makes
+// part of the persistent grid start only when another CTA retires -- a tail as long as the kernel itself (measured at
+// 2 GPUs: 1.34 -> 1.7 ms per SpMV under such a push, 1.44 ms under a copy-engine transfer).
+constexpr int PUSH_TMA_STAGES = 4;
+constexpr int PUSH_TMA_CHUNK = 4096;
+struct PushTma
+{
+    char *dst[8];
+    int n;
+};
+__device__ __forceinline__ uint32_t push_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(32) push_tma_kernel(const __grid_constant__ PushTma fan, const char *__restrict__ src, int64_t bytes16)
+{
+    // bytes16: multiple of 16; chunk i = bytes [i * CHUNK, min((i+1) * CHUNK, bytes16))
+    extern __shared__ __align__(128) unsigned char push_stage[];
+    __shared__ __align__(8) uint64_t full_bar[PUSH_TMA_STAGES];
+    if (threadIdx.x != 0)
+        return;
+    for (int s = 0; s < PUSH_TMA_STAGES; s++)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(push_smem_u32(&full_bar[s])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int64_t nchunks = (bytes16 + PUSH_TMA_CHUNK - 1) / PUSH_TMA_CHUNK;
+    const int64_t G = gridDim.x;
+    auto chunk_bytes = [&](int64_t c) -> uint32_t {
+        const int64_t left = bytes16 - c * PUSH_TMA_CHUNK;
+        return (uint32_t)(left < PUSH_TMA_CHUNK ? left : PUSH_TMA_CHUNK);
+    };
+    auto load = [&](int64_t c, int s) {
+        const uint32_t n = chunk_bytes(c), bar = push_smem_u32(&full_bar[s]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         push_smem_u32(push_stage + (size_t)s * PUSH_TMA_CHUNK)),
+                     "l"(src + c * PUSH_TMA_CHUNK), "r"(n), "r"(bar)
+                     : "memory");
+    };
+    // my chunks: blockIdx.x, blockIdx.x + G, ...; `it` counts them
+    int64_t c_load = blockIdx.x;
+    int it_load = 0;
+    for (; it_load < PUSH_TMA_STAGES - 1 && c_load < nchunks; it_load++, c_load += G)
+        load(c_load, it_load % PUSH_TMA_STAGES);
+    int it = 0;
+    for (int64_t c = blockIdx.x; c < nchunks; c += G, it++)
+    {
+        const int s = it % PUSH_TMA_STAGES;
+        const uint32_t bar = push_smem_u32(&full_bar[s]), parity = (uint32_t)((it / PUSH_TMA_STAGES) & 1);
+        asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\t"
+                     "bra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
+                     "r"(parity)
+                     : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t n = chunk_bytes(c), sm = push_smem_u32(push_stage + (size_t)s * PUSH_TMA_CHUNK);
+        for (int k = 0; k < fan.n; k++)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(fan.dst[k] + c * PUSH_TMA_CHUNK), "r"(sm), "r"(n)
+                         : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // refill the stage the PREVIOUS chunk used: its stores must have read shared memory (not reached the peers)
+        if (c_load < nchunks)
+        {
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            load(c_load, it_load % PUSH_TMA_STAGES);
+            it_load++;
+            c_load += G;
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // every store performed before the kernel ends
+}
+
 // out[i] = (((p_0[i] + p_1[i]) + p_2[i]) + ...), p_k = parts + k * stride: the fixed-order combine of per-rank partial
 // results (column-block TJDS): the same bits whatever order the parts arrived in
 __global__ void __launch_bounds__(256) sum_ordered_kernel(double *__restrict__ out, const double *__restrict__ parts, int nparts,
@@ -524,6 +599,56 @@ extern "C" int smvp_push_fanout_device(void *const *d_dst_list, int n_dst, const
     }
     SMVP_LAUNCH(push_fanout_kernel, (unsigned)ctas, 512, 0, (cudaStream_t)stream, fan, (const double2 *)(src + head), n16,
                 (const double *)(src + head + 16 * n16), tail);
+    SMVP_CUDA(cudaGetLastError());
+    return SMVP_OK;
+}
+
+extern "C" int smvp_push_tma_device(void *const *d_dst_list, int n_dst, const void *d_src, int64_t bytes, int ctas, void *stream)
+{
+    if (bytes < 0 || ctas < 1 || (bytes % 8) != 0 || n_dst < 1 || n_dst > 8 || !d_dst_list || (bytes > 0 && !d_src))
+        return SMVP_E_ARG;
+    if (bytes == 0)
+        return SMVP_OK;
+    const char *src = (const char *)d_src;
+    for (int k = 0; k < n_dst; k++)
+        if (!d_dst_list[k] || ((((uintptr_t)d_dst_list[k]) & 15) != (((uintptr_t)src) & 15)))
+            return smvp_push_fanout_device(d_dst_list, n_dst, d_src, bytes, ctas, stream); // bulk copies need 16-byte alignment
+    int64_t head = (((uintptr_t)src) & 15) ? 8 : 0;
+    if (head > bytes)
+        head = bytes;
+    const int64_t body16 = ((bytes - head) / 16) * 16, tail = bytes - head - body16;
+    PushTma fan;
+    fan.n = n_dst;
+    for (int k = 0; k < 8; k++)
+        fan.dst[k] = k < n_dst ? (char *)d_dst_list[k] + head : nullptr;
+    for (int k = 0; k < n_dst; k++)
+    {
+        if (head)
+            SMVP_CUDA(cudaMemcpyAsync(d_dst_list[k], src, (size_t)head, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        if (tail)
+            SMVP_CUDA(cudaMemcpyAsync((char *)d_dst_list[k] + head + body16, src + head + body16, (size_t)tail, cudaMemcpyDeviceToDevice,
+                                      (cudaStream_t)stream));
+    }
+    if (body16 > 0)
+    {
+        constexpr int SMEM = PUSH_TMA_STAGES * PUSH_TMA_CHUNK;
+        static thread_local int configured_dev = -1;
+        int dev = 0;
+        SMVP_CUDA(cudaGetDevice(&dev));
+        if (configured_dev != dev)
+        {
+            SMVP_CUDA(cudaFuncSetAttribute(push_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+            // same L1 / shared-memory split as the merge-path SpMV (which needs ~200 KB of shared memory per SM): an SM
+            // hosts CTAs of two kernels at once only under one split
+            const char *cv = getenv("SMVP_PUSH_CARVEOUT");
+            if (!(cv && cv[0] == '0'))
+                SMVP_CUDA(cudaFuncSetAttribute(push_tma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                               (int)cudaSharedmemCarveoutMaxShared));
+            configured_dev = dev;
+        }
+        const int64_t nchunks = ceil_div64(body16, PUSH_TMA_CHUNK);
+        SMVP_LAUNCH(push_tma_kernel, (unsigned)(ctas < nchunks ? ctas : nchunks), 32, SMEM, (cudaStream_t)stream, fan, src + head, body16);
+    }
     SMVP_CUDA(cudaGetLastError());
     return SMVP_OK;
 }

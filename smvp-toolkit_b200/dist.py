@@ -325,6 +325,9 @@ class RowBlockCsr:
         "ce_multicast": "ONE copy-engine transfer to the NVSwitch multicast address",
         "sm_multicast": "a small high-priority SM kernel (%d CTAs, 128-bit stores) writing to the NVSwitch multicast address",
         "sm_unicast": "a small high-priority SM kernel (%d CTAs) that reads my rows once and stores them into every peer's y",
+        "tma_unicast": "%d one-warp CTAs driving the TMA engine (cp.async.bulk global->shared->global): my rows are read once "
+                       "and leave for every peer's y as bulk stores over NVLink",
+        "tma_multicast": "%d one-warp CTAs driving the TMA engine (cp.async.bulk) with bulk stores to the NVSwitch multicast address",
     }
 
     def _setup_pipeline(self):
@@ -348,9 +351,9 @@ class RowBlockCsr:
         self._scheme_forced = forced is not None
 
     def scheme_candidates(self):
-        c = ["ce_unicast", "sm_unicast:16", "sm_unicast:32"]
+        c = ["ce_unicast", "tma_unicast:32", "tma_unicast:64", "tma_unicast:128", "sm_unicast:32"]
         if self.mc_base:
-            c += ["ce_multicast", "sm_multicast:8", "sm_multicast:16", "sm_multicast:32", "sm_multicast:64"]
+            c += ["ce_multicast", "sm_multicast:32", "tma_multicast:32", "tma_multicast:64"]
         return c
 
     def set_scheme(self, scheme):
@@ -358,6 +361,10 @@ class RowBlockCsr:
         if kind not in self.SCHEME_HOW or (kind.endswith("multicast") and not self.mc_base):
             raise ValueError("unknown or unavailable pipeline scheme %r" % scheme)
         self.scheme, self.scheme_kind, self.scheme_ctas = scheme, kind, int(arg or 0)
+        # a push done by a kernel runs BESIDE the next step's SpMV: the persistent merge-path grid leaves one CTA slot
+        # per SM free for it (smvp_csr_set_corunner_headroom; measured on one GPU: SpMV 1.34 ms + TMA push 0.42 ms side by
+        # side take 1.78 ms without the room, 1.43 ms with it).  Copy-engine schemes need none.
+        self.A.set_corunner_headroom(0 if kind.startswith("ce_") else 1)
 
     def tune_pipeline(self, stream, steps=6):
         """Times `steps` pipelined steps (exchange drained inside) with every scheme this box offers, takes the MAX over
@@ -387,7 +394,28 @@ class RowBlockCsr:
             t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             res[cand] = float(t[0])
-        best = min(res, key=res.get)
+        # the two fastest are run again over a longer region (a scheme may look good for a handful of steps and lose over
+        # many: the copy-engine multicast did at 8 ranks, 0.70 ms over 6 steps, 0.88 ms over 50) and the better one stays
+        final = {}
+        if len(res) > 1:
+            for cand in sorted(res, key=res.get)[:2]:
+                self.set_scheme(cand)
+                for _ in range(2):
+                    self.step(stream)
+                self.finish(stream)
+                torch.cuda.synchronize()
+                dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(5 * steps):
+                    self.step(stream)
+                self.finish(stream)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                t = torch.tensor([e0.elapsed_time(e1) / (5 * steps)], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                final[cand] = float(t[0])
+        best = min(final, key=final.get) if final else min(res, key=res.get)
         self.set_scheme(best)
         # the two halves of a step, each alone (same MAX over ranks): what the overlap has to hide
         parts = {}
@@ -407,7 +435,7 @@ class RowBlockCsr:
             parts[name] = float(t[0])
         self.symm.barrier(channel=0)
         torch.cuda.synchronize()
-        self.tuning = {"candidates_ms_per_step": res, "chosen": best, **parts}
+        self.tuning = {"candidates_ms_per_step": res, "finalists_ms_per_step_long_run": final, "chosen": best, **parts}
         return self.tuning
 
     def _src(self, b):
@@ -442,6 +470,10 @@ class RowBlockCsr:
             self.eng.copy_device(self.mc_base + off, src, nbytes, ps)
         elif self.scheme_kind == "sm_multicast":
             self.eng.push_device(self.mc_base + off, src, nbytes, self.scheme_ctas, ps)
+        elif self.scheme_kind == "tma_multicast":
+            self.eng.push_tma_device([self.mc_base + off], src, nbytes, self.scheme_ctas, ps)
+        elif self.scheme_kind == "tma_unicast":
+            self.eng.push_tma_device([p + off for p in self.peer_ptrs], src, nbytes, self.scheme_ctas, ps)
         else:  # sm_unicast: one kernel reads my rows once and stores them into every peer's buffer
             self.eng.push_fanout_device([p + off for p in self.peer_ptrs], src, nbytes, self.scheme_ctas, ps)
         with torch.cuda.stream(ps):

@@ -74,6 +74,7 @@ SIGNATURES = {
     "smvp_tjds_build_device": (_int, [_vp, _vp, _vp, _i32, _i32, _i64, _pp]),
     "smvp_csr_set_x_device": (_int, [_vp, _vp, _vp]),
     "smvp_csr_mult_device": (_int, [_vp, _vp, _vp, _int, _vp]),
+    "smvp_csr_set_corunner_headroom": (_int, [_vp, _int]),
     "smvp_csr_mult_device_fanout": (_int, [_vp, _vp, _vp, _int, _int, _vp]),
     "smvp_tjds_set_x_device": (_int, [_vp, _vp, _vp]),
     "smvp_tjds_mult_device": (_int, [_vp, _vp, _int, _i32, _vp]),
@@ -101,6 +102,7 @@ SIGNATURES = {
     "smvp_copy_device": (_int, [_vp, _vp, _i64, _vp]),
     "smvp_push_device": (_int, [_vp, _vp, _i64, _int, _vp]),
     "smvp_push_fanout_device": (_int, [_vp, _int, _vp, _i64, _int, _vp]),
+    "smvp_push_tma_device": (_int, [_vp, _int, _vp, _i64, _int, _vp]),
     "smvp_sum_ordered_device": (_int, [_vp, _vp, _int, _i64, _i64, _vp]),
     "smvp_sum_ordered_ptrs_device": (_int, [_vp, _vp, _int, _i64, _vp]),
     "smvp_flush_l2": (_int, [_i64, _vp]),
@@ -245,6 +247,10 @@ class CsrMatrix:
     def set_x_device(self, d_x, stream=None):
         """Declare the x of the following passes (smvp_csr_set_x_device); pass d_x=None to mult_device afterwards."""
         _check(lib().smvp_csr_set_x_device(self._h, _ptr(d_x), _stream(stream)), "smvp_csr_set_x_device")
+
+    def set_corunner_headroom(self, ctas_per_sm):
+        """Leave room for `ctas_per_sm` CTAs of another kernel per SM beside the persistent merge-path grid."""
+        _check(lib().smvp_csr_set_corunner_headroom(self._h, ctas_per_sm), "smvp_csr_set_corunner_headroom")
 
     def mult_device(self, d_x, d_y, variant=CSR_AUTO, stream=None):
         """One pass y = A x; d_x=None uses the x last given to set_x_device."""
@@ -456,6 +462,11 @@ def push_device(d_dst, d_src, nbytes, ctas=16, stream=None):
 def push_fanout_device(dst_ptrs, d_src, nbytes, ctas=16, stream=None):
     arr = (ctypes.c_void_p * len(dst_ptrs))(*[int(p) for p in dst_ptrs])
     _check(lib().smvp_push_fanout_device(arr, len(dst_ptrs), _ptr(d_src), nbytes, ctas, _stream(stream)), "smvp_push_fanout_device")
+
+
+def push_tma_device(dst_ptrs, d_src, nbytes, ctas=16, stream=None):
+    arr = (ctypes.c_void_p * len(dst_ptrs))(*[int(p) for p in dst_ptrs])
+    _check(lib().smvp_push_tma_device(arr, len(dst_ptrs), _ptr(d_src), nbytes, ctas, _stream(stream)), "smvp_push_tma_device")
 
 
 def sum_ordered_device(d_out, d_parts, nparts, stride, n, stream=None):
