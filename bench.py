@@ -544,6 +544,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from smvp_toolkit_b200 import dist as sdist
 
+    numa_node = sdist.bind_host_near_gpu(local_rank)  # before any page-locked allocation
     ctx = Ctx(torch, dist, eng, sdist, world, rank, local_rank)
     variant_map = {"auto": eng.CSR_AUTO, "vector": eng.CSR_VECTOR, "merge": eng.CSR_MERGE}
     tj_map = {"auto": eng.TJDS_ATOMIC, "atomic": eng.TJDS_ATOMIC, "deterministic": eng.TJDS_DETERMINISTIC}
@@ -644,7 +645,8 @@ def run_ours(args):
         e2e_ms = ctx.max_over_ranks([e2e_ms])[0] / e2e_steps
         # whole-job bytes per step: x crosses PCIe once (each rank uploads its slice), y comes back once
         e2e = {"value": nbytes / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(N * 8),
-               "d2h_bytes_per_step": int(M * 8), "ms_per_step": e2e_ms, "steps": e2e_steps, "api": op.e2e_api}
+               "d2h_bytes_per_step": int(M * 8), "ms_per_step": e2e_ms, "steps": e2e_steps, "api": op.e2e_api,
+               "host_numa_node_of_rank0": numa_node}
         if args.format == "csr":
             # the rows that came back over PCIe against the device-resident result of the same x
             op.step(stream)

@@ -40,6 +40,34 @@ import os
 import numpy as np
 
 
+def bind_host_near_gpu(index):
+    """Pins this process to the CPUs of the NUMA node its GPU hangs off (sysfs), so that the page-locked host vectors it
+    allocates afterwards are local to that GPU's PCIe root.  torchrun starts one process per GPU without any binding;
+    with 8 ranks on a two-socket host half of the host<->device traffic would otherwise cross the socket interconnect.
+    Returns the node, or None when the platform does not say (VMs often report -1)."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:  # noqa: BLE001  (no sysfs, no permission, properties missing: leave the process where it is)
+        return None
+
+
 def balanced_bounds(prefix, total_keys, parts):
     """Boundaries 0 = b_0 <= ... <= b_parts = total_keys with b_g = lower_bound(prefix, g*total/parts),
     where prefix(k) = number of nonzeros with key < k (r_g = lower_bound(row_ptr, g*nnz/G))."""

@@ -620,3 +620,106 @@ def test_full_size_stencil_properties(eng):
     assert torch.equal(y2, yv)
     A.free()
     T.free()
+
+
+def test_full_size_rmat_scale26(eng, monkeypatch):
+    """Configs 3/4 at FULL size (R-MAT scale 26, ~1.06e9 unique entries): where the popularity relabelling, the ranked
+    cache hints, TJDS plans over 1e5+ jagged diagonals and the int32 edge cases actually engage (missing 6).
+      (a) a 2^20-row slice and a 2^20-column slice of the matrix: CSR / TJDS arrays bit-exact against the oracle, the
+          slice's rows of the full y within 1e-12 of the oracle's CSR loop ("arrays bit-exact vs oracle on
+          a <= 1 M-row slice");
+      (b) the relabelled CSR multiply (AUTO picks it here) bit-identical to the natural-order one, merge vs vector
+          within 1e-12;
+      (c) TJDS atomic and deterministic within 1e-12 of CSR on the full matrix; deterministic bit-identical run to run.
+    SMVP_TEST_RMAT_SCALE scales the test down for debugging."""
+    import torch
+
+    scale = int(os.environ.get("SMVP_TEST_RMAT_SCALE", "26"))
+    m = n = 1 << scale
+    r, c, v = eng.synth_rmat(scale, 16 << scale, seed=42)
+    nnz = r.n
+    d_x = torch.empty(n, dtype=torch.float64, device="cuda")
+    eng.synth_vector(d_x, n, 4242)
+    x = d_x.cpu().numpy()
+
+    # ---- (b) full matrix, CSR: AUTO (relabelled at this size) vs natural order
+    A = eng.CsrMatrix.build_device(r, c, v, m, n, nnz)
+    y_auto = torch.empty(m, dtype=torch.float64, device="cuda")
+    A.set_x_device(d_x)
+    A.mult_device(None, y_auto, eng.CSR_MERGE)
+    torch.cuda.synchronize()
+    if scale >= 26:
+        assert A.x_relabel == 1, "AUTO is expected to relabel the column space of R-MAT scale 26"
+    y_vec = torch.empty_like(y_auto)
+    A.mult_device(None, y_vec, eng.CSR_VECTOR)
+    torch.cuda.synchronize()
+    assert float(torch.linalg.norm(y_vec - y_auto) / torch.linalg.norm(y_auto)) <= TOL
+    A.free()
+    monkeypatch.setenv("SMVP_CSR_RELABEL", "0")
+    P = eng.CsrMatrix.build_device(r, c, v, m, n, nnz)
+    y_plain = torch.empty_like(y_auto)
+    P.mult_device(d_x, y_plain, eng.CSR_MERGE)
+    torch.cuda.synchronize()
+    assert P.x_relabel == -1
+    assert torch.equal(y_plain, y_auto), "relabelled and natural-order CSR must agree bit for bit"
+    P.free()
+    monkeypatch.delenv("SMVP_CSR_RELABEL")
+    del y_vec, y_plain
+
+    # ---- (c) full matrix, TJDS
+    T = eng.TjdsMatrix.build_device(r, c, v, m, n, nnz)
+    T.set_x_device(d_x)
+    y_t = torch.empty(m, dtype=torch.float64, device="cuda")
+    T.mult_device(y_t, eng.TJDS_ATOMIC)
+    torch.cuda.synchronize()
+    assert float(torch.linalg.norm(y_t - y_auto) / torch.linalg.norm(y_auto)) <= TOL
+    T.mult_device(y_t, eng.TJDS_DETERMINISTIC)
+    torch.cuda.synchronize()
+    assert float(torch.linalg.norm(y_t - y_auto) / torch.linalg.norm(y_auto)) <= TOL
+    y_t2 = torch.empty_like(y_t)
+    T.mult_device(y_t2, eng.TJDS_DETERMINISTIC)
+    torch.cuda.synchronize()
+    assert torch.equal(y_t, y_t2), "deterministic TJDS differs run to run"
+    assert T.ndiag > 1000
+    T.free()
+    del y_t, y_t2
+
+    # ---- (a) slices against the oracle
+    width = min(1 << 20, m // 4)
+    y_host = y_auto.cpu().numpy()
+
+    def pick(by_col):
+        for start in (m // 2, 3 * (m // 4), m // 4 + m // 8, m // 8):
+            if by_col:
+                blk = eng.coo_filter_device(r, c, v, nnz, 0, m, start, start + width, 0, start)
+            else:
+                blk = eng.coo_filter_device(r, c, v, nnz, start, start + width, 0, n, start, 0)
+            if 1000 <= blk[0].n <= 40_000_000:
+                return start, blk
+            for a in blk:
+                a.free()
+        raise AssertionError("no slice of a testable size")
+
+    r0, (br, bc, bv) = pick(False)
+    coo = oracle.make_coo(torch_view(br).cpu().numpy(), torch_view(bc).cpu().numpy(), torch_view(bv).cpu().numpy())
+    rp, ci, va = oracle.csr_build(coo, width, n)
+    S = eng.CsrMatrix.build_device(br, bc, bv, width, n, br.n)
+    g = S.export()
+    assert np.array_equal(g[0], rp) and np.array_equal(g[1], ci) and np.array_equal(g[2].view(np.int64), va.view(np.int64))
+    S.free()
+    y_ref = oracle.csr_mult(rp, ci, va, x)
+    assert util.rel_l2(y_host[r0:r0 + width], y_ref) <= TOL
+    for a in (br, bc, bv):
+        a.free()
+
+    c0, (br, bc, bv) = pick(True)
+    coo = oracle.make_coo(torch_view(br).cpu().numpy(), torch_view(bc).cpu().numpy(), torch_view(bv).cpu().numpy())
+    t = oracle.tjds_build(coo, m, width)
+    S = eng.TjdsMatrix.build_device(br, bc, bv, m, width, br.n)
+    perm, sp, ri, tv = S.export()
+    assert S.ndiag == t.ndiag
+    assert np.array_equal(perm, t.perm) and np.array_equal(sp, t.start_pos)
+    assert np.array_equal(ri, t.row_ind) and np.array_equal(tv.view(np.int64), t.val.view(np.int64))
+    S.free()
+    for a in (br, bc, bv, r, c, v):
+        a.free()
