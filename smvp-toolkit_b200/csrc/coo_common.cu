@@ -42,8 +42,9 @@ int coo_inspect(const int32_t *d_row, const int32_t *d_col, int64_t nnz, int32_t
     *order = ORDER_ROW_COL;
     if (nnz == 0)
         return SMVP_OK;
-    int *d_flags = nullptr;
-    SMVP_CUDA(dev_alloc(&d_flags, 4));
+    DevTmp flags; // released on every return path
+    SMVP_CUDA(flags.alloc<int>(4));
+    int *d_flags = flags.as<int>();
     SMVP_CUDA(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), s));
     int64_t blocks = ceil_div64(nnz, 256 * 4);
     const int64_t cap = (int64_t)device_props().sms * 16;
@@ -53,7 +54,6 @@ int coo_inspect(const int32_t *d_row, const int32_t *d_col, int64_t nnz, int32_t
     int h[4] = {0, 0, 0, 0};
     SMVP_CUDA(cudaMemcpyAsync(h, d_flags, sizeof(h), cudaMemcpyDeviceToHost, s));
     SMVP_CUDA(cudaStreamSynchronize(s));
-    SMVP_CUDA(cudaFree(d_flags));
     if (h[0])
         return SMVP_E_RANGE;
     *order = !h[1] ? ORDER_ROW_COL : (!h[2] ? ORDER_COL_ROW : ORDER_NONE);
@@ -122,39 +122,34 @@ int coo_sort_index(const int32_t *d_major, const int32_t *d_minor, int64_t nnz, 
     if (blocks > cap)
         blocks = cap;
     const int major_bits = bits_for((uint32_t)n_major), minor_bits = bits_for((uint32_t)n_minor);
-    uint32_t *idx_a = nullptr, *idx_b = nullptr, *res_idx = nullptr;
-    int rc;
-    SMVP_CUDA(dev_alloc(&idx_a, nnz));
-    SMVP_CUDA(dev_alloc(&idx_b, nnz));
+    // every temporary sits in a guard: an allocation or launch failure half-way (a 16 GB build that runs out of memory)
+    // releases what was taken so far; the surviving index buffer is detached from its guard at the end
+    DevTmp g_idx_a, g_idx_b, g_key_a, g_key_b;
+    uint32_t *res_idx = nullptr;
+    SMVP_CUDA(g_idx_a.alloc<uint32_t>(nnz));
+    SMVP_CUDA(g_idx_b.alloc<uint32_t>(nnz));
+    uint32_t *idx_a = g_idx_a.as<uint32_t>(), *idx_b = g_idx_b.as<uint32_t>();
     if (sorted_transposed)
     {
-        uint32_t *key_a = nullptr, *key_b = nullptr, *res_key = nullptr;
-        SMVP_CUDA(dev_alloc(&key_a, nnz));
-        SMVP_CUDA(dev_alloc(&key_b, nnz));
-        SMVP_LAUNCH(make_key32_kernel, (unsigned)blocks, 256, 0, s, d_major, nnz, key_a, idx_a);
+        uint32_t *res_key = nullptr;
+        SMVP_CUDA(g_key_a.alloc<uint32_t>(nnz));
+        SMVP_CUDA(g_key_b.alloc<uint32_t>(nnz));
+        SMVP_LAUNCH(make_key32_kernel, (unsigned)blocks, 256, 0, s, d_major, nnz, g_key_a.as<uint32_t>(), idx_a);
         const int lo = 0, hi = major_bits;
-        rc = radix_sort_pairs<uint32_t>(key_a, idx_a, key_b, idx_b, nnz, &lo, &hi, 1, &res_key, &res_idx, s);
-        cudaFree(key_a);
-        cudaFree(key_b);
+        SMVP_TRY(radix_sort_pairs<uint32_t>(g_key_a.as<uint32_t>(), idx_a, g_key_b.as<uint32_t>(), idx_b, nnz, &lo, &hi, 1, &res_key,
+                                            &res_idx, s));
     }
     else
     {
-        uint64_t *key_a = nullptr, *key_b = nullptr, *res_key = nullptr;
-        SMVP_CUDA(dev_alloc(&key_a, nnz));
-        SMVP_CUDA(dev_alloc(&key_b, nnz));
-        SMVP_LAUNCH(make_key64_kernel, (unsigned)blocks, 256, 0, s, d_major, d_minor, nnz, minor_bits, key_a, idx_a);
+        uint64_t *res_key = nullptr;
+        SMVP_CUDA(g_key_a.alloc<uint64_t>(nnz));
+        SMVP_CUDA(g_key_b.alloc<uint64_t>(nnz));
+        SMVP_LAUNCH(make_key64_kernel, (unsigned)blocks, 256, 0, s, d_major, d_minor, nnz, minor_bits, g_key_a.as<uint64_t>(), idx_a);
         const int lo = 0, hi = major_bits + minor_bits;
-        rc = radix_sort_pairs<uint64_t>(key_a, idx_a, key_b, idx_b, nnz, &lo, &hi, 1, &res_key, &res_idx, s);
-        cudaFree(key_a);
-        cudaFree(key_b);
+        SMVP_TRY(radix_sort_pairs<uint64_t>(g_key_a.as<uint64_t>(), idx_a, g_key_b.as<uint64_t>(), idx_b, nnz, &lo, &hi, 1, &res_key,
+                                            &res_idx, s));
     }
-    if (rc != SMVP_OK)
-    {
-        cudaFree(idx_a);
-        cudaFree(idx_b);
-        return rc;
-    }
-    cudaFree(res_idx == idx_a ? idx_b : idx_a);
+    (res_idx == idx_a ? g_idx_a : g_idx_b).p = nullptr; // handed to the caller
     *d_idx = res_idx;
     return SMVP_OK;
 }

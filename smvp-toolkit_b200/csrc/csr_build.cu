@@ -35,6 +35,7 @@ static void csr_release(smvp_csr *A)
     cudaFree(A->tile_row);
     cudaFree(A->head_val);
     cudaFree(A->carry_val);
+    cudaFree(A->warps_done);
     cudaFree(A->d_x);
     cudaFree(A->d_y);
     csr_pipe_release(A);
@@ -57,13 +58,13 @@ static int csr_build_impl(const int32_t *d_row, const int32_t *d_col, const doub
     // row counts -> row_ptr by exclusive scan; row_ptr[rows] = nnz
     SMVP_TRY(histogram_i32(d_row, nnz, (uint32_t *)A->row_ptr, (int64_t)rows + 1, s));
     {
-        uint32_t *d_max = nullptr;
-        SMVP_CUDA(dev_alloc(&d_max, 1));
+        DevTmp g_max;
+        SMVP_CUDA(g_max.alloc<uint32_t>(1));
+        uint32_t *d_max = g_max.as<uint32_t>();
         SMVP_TRY(max_u32((const uint32_t *)A->row_ptr, rows, d_max, s));
         uint32_t h = 0;
         SMVP_CUDA(cudaMemcpyAsync(&h, d_max, sizeof(h), cudaMemcpyDeviceToHost, s));
         SMVP_CUDA(cudaStreamSynchronize(s));
-        SMVP_CUDA(cudaFree(d_max));
         A->max_row_nnz = (int32_t)h;
     }
     SMVP_TRY(exclusive_scan_u32((const uint32_t *)A->row_ptr, (uint32_t *)A->row_ptr, rows, nullptr, s));
@@ -71,6 +72,8 @@ static int csr_build_impl(const int32_t *d_row, const int32_t *d_col, const doub
 
     uint32_t *d_idx = nullptr;
     SMVP_TRY(coo_sort_index(d_row, d_col, nnz, rows, cols, order == ORDER_ROW_COL, order == ORDER_COL_ROW, &d_idx, s));
+    DevTmp g_idx;
+    g_idx.p = d_idx; // released on every return path below
     if (d_idx == nullptr)
     {
         if (nnz > 0)
@@ -88,7 +91,6 @@ static int csr_build_impl(const int32_t *d_row, const int32_t *d_col, const doub
         SMVP_LAUNCH(gather_csr_kernel, (unsigned)blocks, 256, 0, s, (const uint32_t *)d_idx, d_col, d_val, nnz, A->col_ind,
                     A->val);
         SMVP_CUDA(cudaStreamSynchronize(s));
-        SMVP_CUDA(cudaFree(d_idx));
     }
     SMVP_CUDA(cudaStreamSynchronize(s));
     SMVP_CUDA(cudaGetLastError());

@@ -406,6 +406,40 @@ __device__ __forceinline__ TileView make_tile(int32_t r0, int32_t r1, int32_t t,
     return v;
 }
 
+// First row of a tile that ends a row there: y[row] = (carries of the tiles the row crossed, in tile order) + (partial
+// of the tile where it ends).  tile_row[u+1] is the row tile u's carry belongs to.
+template <bool FANOUT>
+__device__ __forceinline__ void merge_fixup_tile(int32_t t, const int32_t *__restrict__ tile_row, const double *__restrict__ head_val,
+                                                 const double *__restrict__ carry_val, double *__restrict__ y, const YFan &fan)
+{
+    // everything the common case needs is loaded up front (independent loads: one memory round trip)
+    const int32_t r = tile_row[t];
+    const int32_t r_next = tile_row[t + 1];
+    const int32_t r_prev = t > 0 ? tile_row[t - 1] : -1;
+    const double c_prev = t > 0 ? __ldcg(carry_val + t - 1) : 0.0; // L2 loads: another SM wrote these in this launch
+    const double h = __ldcg(head_val + t);
+    if (r_next == r)
+        return; // no row ends in this tile
+    double acc;
+    if (t == 0)
+        acc = h;
+    else if (r_prev != r)
+        acc = __dadd_rn(c_prev, h); // the row was cut once: tile t-1 carries into it
+    else
+    {
+        int32_t u = t - 1; // the row spans several tiles: carries of tiles [u, t-1], in tile order
+        while (u > 0 && tile_row[u] == r)
+            u--;
+        if (tile_row[u + 1] != r)
+            u++;
+        acc = __ldcg(carry_val + u);
+        for (int32_t k = u + 1; k < t; k++)
+            acc = __dadd_rn(acc, __ldcg(carry_val + k));
+        acc = __dadd_rn(acc, h);
+    }
+    store_y<FANOUT>(y, fan, r, acc);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Warp-autonomous merge-path: the unit of work is a WARP tile of 32*IPT merge items.  Every warp owns
 // its shared-memory stage(s) and its mbarrier, fetches its tiles with its own TMA bulk copies and
@@ -417,7 +451,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     csr_merge_warp_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_ind, const double *__restrict__ val,
                           const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int32_t rows,
                           int64_t nnz, int32_t tile_begin, int32_t num_tiles, double *__restrict__ head_val,
-                          double *__restrict__ carry_val, const __grid_constant__ YFan fan, int32_t hot_l1, int32_t hot_l2)
+                          double *__restrict__ carry_val, const __grid_constant__ YFan fan, int32_t hot_l1, int32_t hot_l2,
+                          uint32_t *__restrict__ warps_done)
 {
     // processes tiles [tile_begin, num_tiles): a sub-range lets the host overlap the copy-out of finished rows
     static_assert(STAGES == 1, "one stage per warp: deeper rings lost to more resident warps in every sweep");
@@ -686,10 +721,27 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             break; // 32-bit overflow guard
         t = tn;
     }
+    // Small matrices (warps_done != NULL): the fix-up of rows cut by tile boundaries is done by the LAST warp of the grid
+    // to finish instead of by a second launch -- in the batched `-n` loop of a matrix like memplus a launch costs as
+    // much as the multiply.  Release / acquire through the counter; the counter is left at zero for the next pass.
+    if (warps_done != nullptr)
+    {
+        __threadfence();
+        uint32_t last = 0;
+        if (lane == 0)
+            last = atomicAdd(warps_done, 1u) == (uint32_t)gridDim.x * WARPS - 1u;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last)
+        {
+            __threadfence();
+            for (int32_t u = tile_begin + lane; u < num_tiles; u += 32)
+                merge_fixup_tile<FANOUT>(u, tile_row, head_val, carry_val, y, fan);
+            if (lane == 0)
+                *warps_done = 0u;
+        }
+    }
 }
 
-// First row of every tile that ends a row there: y[row] = (carries of the tiles the row crossed, in tile
-// order) + (partial of the tile where it ends).  tile_row[u+1] is the row tile u's carry belongs to.
 template <bool FANOUT>
 __global__ void __launch_bounds__(256) merge_fixup_kernel(const int32_t *__restrict__ tile_row, const double *__restrict__ head_val,
                                                           const double *__restrict__ carry_val, int32_t tile_begin,
@@ -697,34 +749,8 @@ __global__ void __launch_bounds__(256) merge_fixup_kernel(const int32_t *__restr
                                                           const __grid_constant__ YFan fan)
 {
     const int32_t t = tile_begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= num_tiles)
-        return;
-    // everything the common case needs is loaded up front (independent loads: one memory round trip)
-    const int32_t r = tile_row[t];
-    const int32_t r_next = tile_row[t + 1];
-    const int32_t r_prev = t > 0 ? tile_row[t - 1] : -1;
-    const double c_prev = t > 0 ? carry_val[t - 1] : 0.0;
-    const double h = head_val[t];
-    if (r_next == r)
-        return; // no row ends in this tile
-    double acc;
-    if (t == 0)
-        acc = h;
-    else if (r_prev != r)
-        acc = __dadd_rn(c_prev, h); // the row was cut once: tile t-1 carries into it
-    else
-    {
-        int32_t u = t - 1; // the row spans several tiles: carries of tiles [u, t-1], in tile order
-        while (u > 0 && tile_row[u] == r)
-            u--;
-        if (tile_row[u + 1] != r)
-            u++;
-        acc = carry_val[u];
-        for (int32_t k = u + 1; k < t; k++)
-            acc = __dadd_rn(acc, carry_val[k]);
-        acc = __dadd_rn(acc, h);
-    }
-    store_y<FANOUT>(y, fan, r, acc);
+    if (t < num_tiles)
+        merge_fixup_tile<FANOUT>(t, tile_row, head_val, carry_val, y, fan);
 }
 
 // ---- the instantiations AUTO chooses from: {warps per CTA, items per thread, stages per warp, min CTAs/SM}.
@@ -749,6 +775,8 @@ static int pick_merge_cfg(const smvp_csr *A)
     return 2;     // 14 items per thread (two lanes per 27-point-stencil row), 4 warps per CTA
 }
 
+constexpr int32_t MERGE_FUSED_FIXUP_TILES = 4096;
+
 static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
 {
     const int32_t tile_items = wmerge_tile_items(cfg);
@@ -757,6 +785,8 @@ static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
     cudaFree(A->tile_row);
     cudaFree(A->head_val);
     cudaFree(A->carry_val);
+    cudaFree(A->warps_done);
+    A->warps_done = nullptr;
     A->tile_row = nullptr;
     A->head_val = A->carry_val = nullptr;
     A->merge_cfg = -1;
@@ -768,6 +798,11 @@ static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
     SMVP_CUDA(dev_alloc(&A->tile_row, tiles + 1));
     SMVP_CUDA(dev_alloc(&A->head_val, tiles));
     SMVP_CUDA(dev_alloc(&A->carry_val, tiles));
+    if (!A->warps_done && getenv("SMVP_NO_FUSED_FIXUP") == nullptr)
+    {
+        SMVP_CUDA(dev_alloc(&A->warps_done, 1));
+        SMVP_CUDA(cudaMemsetAsync(A->warps_done, 0, sizeof(uint32_t), s));
+    }
     SMVP_LAUNCH(merge_plan_kernel, (unsigned)ceil_div64(tiles + 1, 256), 256, 0, s, A->row_ptr, A->rows, A->nnz, tile_items,
                 (int32_t)tiles, A->tile_row);
     SMVP_CUDA(cudaGetLastError());
@@ -841,10 +876,14 @@ static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, cons
         grid = need;
     if (grid > 0)
     {
+        // few tiles: the last warp to finish does the fix-up (one launch per pass instead of two)
+        uint32_t *done = (ntiles <= MERGE_FUSED_FIXUP_TILES && A->warps_done && tile_begin == 0 && tile_end == A->merge_tiles)
+                             ? A->warps_done : nullptr;
         SMVP_LAUNCH(kern, (unsigned)grid, WARPS * 32, SMEM, s, A->row_ptr, mult_cols(A), A->val, d_x, d_y, A->tile_row, A->rows,
-                    A->nnz, tile_begin, tile_end, A->head_val, A->carry_val, fan, hot_l1, hot_l2);
-        SMVP_LAUNCH(merge_fixup_kernel<FANOUT>, (unsigned)ceil_div64(ntiles, 256), 256, 0, s, (const int32_t *)A->tile_row,
-                    (const double *)A->head_val, (const double *)A->carry_val, tile_begin, tile_end, d_y, fan);
+                    A->nnz, tile_begin, tile_end, A->head_val, A->carry_val, fan, hot_l1, hot_l2, done);
+        if (!done)
+            SMVP_LAUNCH(merge_fixup_kernel<FANOUT>, (unsigned)ceil_div64(ntiles, 256), 256, 0, s, (const int32_t *)A->tile_row,
+                        (const double *)A->head_val, (const double *)A->carry_val, tile_begin, tile_end, d_y, fan);
     }
     return SMVP_OK;
 }

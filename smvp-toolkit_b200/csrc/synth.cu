@@ -399,21 +399,26 @@ extern "C" int smvp_synth_stencil27(int32_t nx, int32_t ny, int32_t nz, int64_t 
     *nnz = n;
     *d_row = *d_col = nullptr;
     *d_val = nullptr;
-    uint32_t *offs = nullptr;
-    SMVP_CUDA(dev_alloc(&offs, nrows));
-    SMVP_CUDA(dev_alloc(d_row, n));
-    SMVP_CUDA(dev_alloc(d_col, n));
-    SMVP_CUDA(dev_alloc(d_val, n));
+    DevTmp g_offs, g_row, g_col, g_val; // the outputs are detached from their guards only on success
+    SMVP_CUDA(g_offs.alloc<uint32_t>(nrows));
+    SMVP_CUDA(g_row.alloc<int32_t>(n));
+    SMVP_CUDA(g_col.alloc<int32_t>(n));
+    SMVP_CUDA(g_val.alloc<double>(n));
+    uint32_t *offs = g_offs.as<uint32_t>();
     if (nrows > 0)
     {
         const unsigned blocks = (unsigned)ceil_div64(nrows, 256);
         SMVP_LAUNCH(stencil_count_kernel, blocks, 256, 0, 0, nx, ny, nz, row_begin, nrows, offs);
         SMVP_TRY(exclusive_scan_u32(offs, offs, nrows, nullptr, 0));
         SMVP_LAUNCH(stencil_fill_kernel, blocks, 256, 0, 0, nx, ny, nz, row_begin, nrows, (const uint32_t *)offs, value_mode, seed,
-                    *d_row, *d_col, *d_val);
+                    g_row.as<int32_t>(), g_col.as<int32_t>(), g_val.as<double>());
     }
     SMVP_CUDA(cudaDeviceSynchronize());
-    SMVP_CUDA(cudaFree(offs));
+    SMVP_CUDA(cudaGetLastError());
+    *d_row = g_row.as<int32_t>();
+    *d_col = g_col.as<int32_t>();
+    *d_val = g_val.as<double>();
+    g_row.p = g_col.p = g_val.p = nullptr;
     return SMVP_OK;
 }
 

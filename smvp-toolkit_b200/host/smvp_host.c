@@ -575,7 +575,7 @@ static int write_vector_parallel(FILE *f, const double *y, int rows)
             rc = -2; /* partial output: do not let the caller append the vector a second time */
     for (k = 0; k < n; k++)
         free(blk[k].buf);
-    return rc == -2 ? 0 : rc;
+    return rc; /* -1: nothing written, the caller may format sequentially; -2: a short write (disk full) -- an error */
 }
 
 int smvp_write_report(const char *input_file_name, const char *report_dir, const char *alg_name, int nnz, int rows,
@@ -624,16 +624,23 @@ int smvp_write_report(const char *input_file_name, const char *report_dir, const
     fprintf(f, "Time StDev: %g ms\n\n", t->time_stdev);
     fprintf(f, "Output vector (one cell per line):\n");
     fprintf(f, "[\n");
-    if (rows >= REPORT_PARALLEL_ROWS && write_vector_parallel(f, y, rows) == 0)
+    if (rows >= REPORT_PARALLEL_ROWS)
     {
-        fclose(f);
-        return 0;
+        const int prc = write_vector_parallel(f, y, rows);
+        if (prc == 0 || prc == -2)
+        {
+            /* a short write, a failed flush or a failed close (ENOSPC, EIO) is an error: never report "saved" then */
+            const int bad = prc == -2 || ferror(f);
+            return (fclose(f) != 0 || bad) ? -1 : 0;
+        }
     }
     for (i = 0; i < rows; i++)
     {
         fprintf(f, "%g", y[i]);
         fprintf(f, i < rows - 1 ? "\n" : "\n]\n\n");
     }
-    fclose(f);
-    return 0;
+    {
+        const int bad = ferror(f);
+        return (fclose(f) != 0 || bad) ? -1 : 0;
+    }
 }
