@@ -157,7 +157,6 @@ struct smvp_csr
     int32_t *tile_row;      // [merge_tiles+1] rows consumed before each tile
     double *head_val;       // [merge_tiles] partial of the first row that ends in the tile
     double *carry_val;      // [merge_tiles] partial of the row that continues past the tile
-    uint32_t *warps_done;   // [1] finished-warp counter of the fused fix-up (few tiles: last warp of the grid does it)
     // scratch for the host-vector entry point
     double *d_x, *d_y;
     // plan of the pipelined host-vector pass (csr_mult.cu): tile ranges, the rows each completes and how much of x

@@ -35,7 +35,6 @@ static void csr_release(smvp_csr *A)
     cudaFree(A->tile_row);
     cudaFree(A->head_val);
     cudaFree(A->carry_val);
-    cudaFree(A->warps_done);
     cudaFree(A->d_x);
     cudaFree(A->d_y);
     csr_pipe_release(A);

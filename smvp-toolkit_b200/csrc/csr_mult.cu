@@ -452,8 +452,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                           const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int32_t rows,
                           int64_t nnz, int32_t tile_begin, int32_t num_tiles, double *__restrict__ head_val,
                           double *__restrict__ carry_val, const __grid_constant__ YFan fan, int32_t hot_l1, int32_t hot_l2,
-                          uint32_t *__restrict__ warps_done)
+                          int32_t early_dependents)
 {
+    // Small grids (early_dependents != 0): let the fix-up kernel, launched with programmatic stream serialization, be
+    // scheduled NOW; it parks at griddepcontrol.wait until this grid has completed and flushed.  In the batched `-n` loop
+    // of a matrix like memplus that hides the second launch's latency (a pass lasts as long as a launch).
+    if (early_dependents)
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // processes tiles [tile_begin, num_tiles): a sub-range lets the host overlap the copy-out of finished rows
     static_assert(STAGES == 1, "one stage per warp: deeper rings lost to more resident warps in every sweep");
     using Shape = MergeShape<32, IPT, 1>;
@@ -721,25 +726,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             break; // 32-bit overflow guard
         t = tn;
     }
-    // Small matrices (warps_done != NULL): the fix-up of rows cut by tile boundaries is done by the LAST warp of the grid
-    // to finish instead of by a second launch -- in the batched `-n` loop of a matrix like memplus a launch costs as
-    // much as the multiply.  Release / acquire through the counter; the counter is left at zero for the next pass.
-    if (warps_done != nullptr)
-    {
-        __threadfence();
-        uint32_t last = 0;
-        if (lane == 0)
-            last = atomicAdd(warps_done, 1u) == (uint32_t)gridDim.x * WARPS - 1u;
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last)
-        {
-            __threadfence();
-            for (int32_t u = tile_begin + lane; u < num_tiles; u += 32)
-                merge_fixup_tile<FANOUT>(u, tile_row, head_val, carry_val, y, fan);
-            if (lane == 0)
-                *warps_done = 0u;
-        }
-    }
 }
 
 template <bool FANOUT>
@@ -748,6 +734,8 @@ __global__ void __launch_bounds__(256) merge_fixup_kernel(const int32_t *__restr
                                                           int32_t num_tiles, double *__restrict__ y,
                                                           const __grid_constant__ YFan fan)
 {
+    // no-op unless launched with programmatic stream serialization: then it waits here for the merge kernel's results
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int32_t t = tile_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (t < num_tiles)
         merge_fixup_tile<FANOUT>(t, tile_row, head_val, carry_val, y, fan);
@@ -775,7 +763,7 @@ static int pick_merge_cfg(const smvp_csr *A)
     return 2;     // 14 items per thread (two lanes per 27-point-stencil row), 4 warps per CTA
 }
 
-constexpr int32_t MERGE_FUSED_FIXUP_TILES = 4096;
+constexpr int32_t MERGE_PDL_TILES = 8192; // grids of at most this many warp tiles launch their fix-up early
 
 static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
 {
@@ -785,8 +773,6 @@ static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
     cudaFree(A->tile_row);
     cudaFree(A->head_val);
     cudaFree(A->carry_val);
-    cudaFree(A->warps_done);
-    A->warps_done = nullptr;
     A->tile_row = nullptr;
     A->head_val = A->carry_val = nullptr;
     A->merge_cfg = -1;
@@ -798,11 +784,6 @@ static int merge_plan(smvp_csr *A, int cfg, cudaStream_t s)
     SMVP_CUDA(dev_alloc(&A->tile_row, tiles + 1));
     SMVP_CUDA(dev_alloc(&A->head_val, tiles));
     SMVP_CUDA(dev_alloc(&A->carry_val, tiles));
-    if (!A->warps_done && getenv("SMVP_NO_FUSED_FIXUP") == nullptr)
-    {
-        SMVP_CUDA(dev_alloc(&A->warps_done, 1));
-        SMVP_CUDA(cudaMemsetAsync(A->warps_done, 0, sizeof(uint32_t), s));
-    }
     SMVP_LAUNCH(merge_plan_kernel, (unsigned)ceil_div64(tiles + 1, 256), 256, 0, s, A->row_ptr, A->rows, A->nnz, tile_items,
                 (int32_t)tiles, A->tile_row);
     SMVP_CUDA(cudaGetLastError());
@@ -876,12 +857,32 @@ static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, cons
         grid = need;
     if (grid > 0)
     {
-        // few tiles: the last warp to finish does the fix-up (one launch per pass instead of two)
-        uint32_t *done = (ntiles <= MERGE_FUSED_FIXUP_TILES && A->warps_done && tile_begin == 0 && tile_end == A->merge_tiles)
-                             ? A->warps_done : nullptr;
+        // (a fix-up fused into the kernel -- the last warp of the grid to finish walks the tiles -- was tried for the
+        // batched `-n` loop of small matrices: one warp serialises the few hundred tiles of a matrix like memplus,
+        // 12.1 us per pass against 5.7 us with the second launch.  Two launches it stays.)
+        static thread_local int pdl_ok = -1; // SMVP_NO_PDL=1 switches the early launch of the fix-up off
+        if (pdl_ok < 0)
+            pdl_ok = getenv("SMVP_NO_PDL") == nullptr ? 1 : 0;
+        const bool early = pdl_ok == 1 && ntiles <= MERGE_PDL_TILES;
         SMVP_LAUNCH(kern, (unsigned)grid, WARPS * 32, SMEM, s, A->row_ptr, mult_cols(A), A->val, d_x, d_y, A->tile_row, A->rows,
-                    A->nnz, tile_begin, tile_end, A->head_val, A->carry_val, fan, hot_l1, hot_l2, done);
-        if (!done)
+                    A->nnz, tile_begin, tile_end, A->head_val, A->carry_val, fan, hot_l1, hot_l2, early ? 1 : 0);
+        if (early)
+        {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)ceil_div64(ntiles, 256));
+            cfg.blockDim = dim3(256);
+            cfg.dynamicSmemBytes = 0;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            SMVP_CUDA(cudaLaunchKernelEx(&cfg, merge_fixup_kernel<FANOUT>, (const int32_t *)A->tile_row, (const double *)A->head_val,
+                                         (const double *)A->carry_val, tile_begin, tile_end, d_y, fan));
+            ::smvp::g_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+        else
             SMVP_LAUNCH(merge_fixup_kernel<FANOUT>, (unsigned)ceil_div64(ntiles, 256), 256, 0, s, (const int32_t *)A->tile_row,
                         (const double *)A->head_val, (const double *)A->carry_val, tile_begin, tile_end, d_y, fan);
     }
