@@ -53,7 +53,7 @@ def parse_args():
     p.add_argument("--scale", type=int, default=26, help="rmat: log2(rows)")
     p.add_argument("--edge-factor", type=int, default=16)
     p.add_argument("--format", default="csr", choices=["csr", "tjds"])
-    p.add_argument("--variant", default="auto", choices=["auto", "vector", "merge", "atomic", "deterministic"])
+    p.add_argument("--variant", default="auto", choices=["auto", "vector", "merge", "atomic", "deterministic", "fast"])
     p.add_argument("--exchange", default="auto", choices=["auto", "pipeline", "copy", "multicast", "p2p", "nccl", "none"],
                    help="N>1: collective after the multiply (allgather of y for CSR, reduce-scatter for TJDS)")
     p.add_argument("--sub-blocks", type=int, default=4, help="exchange=copy: sub-blocks per rank")
@@ -482,11 +482,13 @@ def run_secondary(ctx, args, stencil_gen, y_stencil_csr, x_stencil):
         out.append(d)
 
     # ---- stencil TJDS, atomic and deterministic (configs[2] names both formats)
-    for vname, variant in (("atomic", eng.TJDS_ATOMIC), ("deterministic", eng.TJDS_DETERMINISTIC)):
+    tjds_variants = (("atomic", eng.TJDS_ATOMIC), ("deterministic", eng.TJDS_DETERMINISTIC),
+                     ("deterministic_fast", eng.TJDS_DETERMINISTIC_FAST))
+    for vname, variant in tjds_variants:
         op = sdist.ColBlockTjds(eng, stencil_gen, ctx.rank, ctx.world, variant, exchange=exch_tjds)
         op.set_x(x_stencil, ctx.stream)
         t = timed_steps(ctx, op, steps, 3)
-        parity = check_tjds_parity(ctx, op, y_stencil_csr, variant == eng.TJDS_DETERMINISTIC)
+        parity = check_tjds_parity(ctx, op, y_stencil_csr, variant != eng.TJDS_ATOMIC)
         record("stencil 369^3 TJDS %s" % vname if args.grid == 369 else "stencil %d^3 TJDS %s" % (args.grid, vname),
                "configs[2]", op, t, parity, {"ndiag": op.ndiag, "tjds_plan": dict(zip(("skewed_walk", "det_route"), op.T.plan()))})
         op.free()
@@ -513,11 +515,11 @@ def run_secondary(ctx, args, stencil_gen, y_stencil_csr, x_stencil):
     op.free()
     del op
     torch.cuda.empty_cache()
-    for vname, variant in (("atomic", eng.TJDS_ATOMIC), ("deterministic", eng.TJDS_DETERMINISTIC)):
+    for vname, variant in tjds_variants:
         op = sdist.ColBlockTjds(eng, gen, ctx.rank, ctx.world, variant, exchange=exch_tjds)
         op.set_x(x, ctx.stream)
         t = timed_steps(ctx, op, steps, 3)
-        parity = check_tjds_parity(ctx, op, y_csr, variant == eng.TJDS_DETERMINISTIC)
+        parity = check_tjds_parity(ctx, op, y_csr, variant != eng.TJDS_ATOMIC)
         record("R-MAT scale %d TJDS %s" % (scale, vname), "configs[4]", op, t, parity,
                {"ndiag": op.ndiag, "tjds_plan": dict(zip(("skewed_walk", "det_route"), op.T.plan()))})
         op.free()
@@ -547,7 +549,8 @@ def run_ours(args):
     numa_node = sdist.bind_host_near_gpu(local_rank)  # before any page-locked allocation
     ctx = Ctx(torch, dist, eng, sdist, world, rank, local_rank)
     variant_map = {"auto": eng.CSR_AUTO, "vector": eng.CSR_VECTOR, "merge": eng.CSR_MERGE}
-    tj_map = {"auto": eng.TJDS_ATOMIC, "atomic": eng.TJDS_ATOMIC, "deterministic": eng.TJDS_DETERMINISTIC}
+    tj_map = {"auto": eng.TJDS_ATOMIC, "atomic": eng.TJDS_ATOMIC, "deterministic": eng.TJDS_DETERMINISTIC,
+              "fast": eng.TJDS_DETERMINISTIC_FAST}
     primary_default = args.workload == "stencil27" and args.format == "csr"
 
     # ---------------- build the shard of this rank
@@ -601,7 +604,7 @@ def run_ours(args):
         ref_op.step(stream)
         ref_op.finish(stream)
         ctx.barrier()
-        parity = check_tjds_parity(ctx, op, ref_op.last_y(), tj_map.get(args.variant) == eng.TJDS_DETERMINISTIC)
+        parity = check_tjds_parity(ctx, op, ref_op.last_y(), tj_map.get(args.variant, eng.TJDS_ATOMIC) != eng.TJDS_ATOMIC)
         ref_op.free()
         del ref_op
 

@@ -64,7 +64,18 @@ typedef struct smvp_tjds smvp_tjds; /* opaque: TJDSData (main-cli.c:70-75) resid
 
 /* TJDS multiply variants */
 #define SMVP_TJDS_ATOMIC 0        /* coalesced jagged-diagonal streaming, fp64 atomicAdd scatter into y */
-#define SMVP_TJDS_DETERMINISTIC 1 /* order-independent exact accumulation: bit-identical run to run  */
+#define SMVP_TJDS_DETERMINISTIC 1 /* order-independent exact INTEGER accumulation: every product is split exactly into two
+                                     64-bit fixed-point words scaled per row by a bound known before the multiply
+                                     (row_exp + exponent of max|x|), the words are added with integer atomics, one final
+                                     rounding: y is the CORRECTLY ROUNDED row sum, bit-identical run to run (and between
+                                     the straight and the skewed walk, with and without row relabelling).            */
+#define SMVP_TJDS_DETERMINISTIC_FAST 2 /* the same with the high word only: a product is truncated toward zero at 2^-62 of
+                                     its row's bound B_r = 2^ceil(log2(max|a_rj| * max|x| * count_r)).  Just as
+                                     reproducible (integer sums), one reduction per run and half the accumulator traffic;
+                                     the error is bounded NORMWISE, |err_r| <= count_r * 2^-62 * B_r -- 2^-9 of what one
+                                     fp64 addition at magnitude B_r rounds away -- not relative to |y_r|: an x whose
+                                     entries span many orders of magnitude can cost a row with small products digits
+                                     that the exact variant keeps.                                                  */
 
 /* ---- statistics of the per-iteration times: struct _time_data_ (main-cli.c:87-95), same field order */
 typedef struct smvp_time_stats_t
@@ -156,7 +167,7 @@ typedef struct smvp_tjds_info_t
     int32_t input_order;
     int64_t bytes_per_mult;   /* 12 nnz + 4 (ndiag+1) + 8 cols + 8 rows                         */
     int64_t device_bytes;
-    int32_t launches_per_mult[2]; /* indexed by variant; includes the zero-fill of y            */
+    int32_t launches_per_mult[3]; /* indexed by variant; includes the zero-fill of y            */
     int32_t y_relabel;        /* multiply plan: 1 = the kernels scatter through popularity-relabelled row
                                  indices and a last pass restores the row order of y, -1 = natural order,
                                  0 = not decided yet (decided at the first pass)                  */

@@ -28,6 +28,15 @@
 namespace smvp
 {
 
+static int env_int_early(const char *name, int dflt, int lo, int hi)
+{
+    const char *e = getenv(name);
+    if (!e || !e[0])
+        return dflt;
+    const int v = atoi(e);
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -809,15 +818,6 @@ static void hot_limits(int32_t *l1, int32_t *l2)
     *l2 = e2 && e2[0] ? atoi(e2) : (4 << 20); // 32 MB
 }
 
-static int env_int_early(const char *name, int dflt, int lo, int hi)
-{
-    const char *e = getenv(name);
-    if (!e || !e[0])
-        return dflt;
-    const int v = atoi(e);
-    return v < lo ? lo : (v > hi ? hi : v);
-}
-
 template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT, bool RANKED, bool UNI>
 static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, const YFan *fanp, cudaStream_t s, int32_t tile_begin,
                          int32_t tile_end)
@@ -959,6 +959,45 @@ static int csr_mult_launch(smvp_csr *A, const double *x, double *d_y, const YFan
     return SMVP_OK;
 }
 
+// L2 persisting carve-out for the hot prefix of a relabelled x (tuning hook SMVP_L2_PERSIST_MB, off by default): the
+// top-ranked entries of x_rel are declared "persisting" for the stream of the pass, everything else streams.
+static int l2_persist_window(cudaStream_t s, const void *base, size_t bytes)
+{
+    static thread_local int dev_done = -1;
+    static thread_local size_t max_win = 0, max_persist = 0;
+    int dev = 0;
+    SMVP_CUDA(cudaGetDevice(&dev));
+    if (dev_done != dev)
+    {
+        int v = 0;
+        SMVP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+        max_win = (size_t)v;
+        SMVP_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, dev));
+        max_persist = (size_t)v;
+        dev_done = dev;
+    }
+    cudaStreamAttrValue attr = {};
+    if (bytes > 0)
+    {
+        if (bytes > max_win)
+            bytes = max_win;
+        SMVP_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes < max_persist ? bytes : max_persist));
+        attr.accessPolicyWindow.base_ptr = const_cast<void *>(base);
+        attr.accessPolicyWindow.num_bytes = bytes;
+        attr.accessPolicyWindow.hitRatio = bytes <= max_persist ? 1.0f : (float)max_persist / (float)bytes;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    }
+    else
+    {
+        attr.accessPolicyWindow.num_bytes = 0;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    }
+    SMVP_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &attr));
+    return SMVP_OK;
+}
+
 static int csr_mult_any(smvp_csr *A, const double *d_x, double *d_y, const YFan *fan, int variant, void *stream)
 {
     if (variant != SMVP_CSR_AUTO && variant != SMVP_CSR_VECTOR && variant != SMVP_CSR_MERGE)
@@ -982,7 +1021,13 @@ static int csr_mult_any(smvp_csr *A, const double *d_x, double *d_y, const YFan 
         if (!x && A->cols > 0)
             return SMVP_E_ARG;
     }
-    return csr_mult_launch(A, x, d_y, fan, variant, s);
+    const int persist_mb = A->relabel_state == 1 ? env_int_early("SMVP_L2_PERSIST_MB", 0, 0, 4096) : 0;
+    if (persist_mb > 0)
+        SMVP_TRY(l2_persist_window(s, x, (size_t)persist_mb << 20));
+    const int rc = csr_mult_launch(A, x, d_y, fan, variant, s);
+    if (persist_mb > 0)
+        SMVP_TRY(l2_persist_window(s, nullptr, 0));
+    return rc;
 }
 
 extern "C" int smvp_csr_set_x_device(smvp_csr *A, const double *d_x, void *stream)

@@ -380,8 +380,16 @@ __device__ __forceinline__ double pow2_f64(int32_t e) { return __hiloint2double(
 // FAST: the host has checked (tjds_det_route) that every row bound T lies in the range of fixed_split_fast and that
 // no visited row lacks an exponent, so the per-entry "is the product zero / which split" tests and the 60-instruction
 // general split disappear from the loop.  Both instantiations produce the same words, hence the same bits of y.
+// WORDS = 2 (SMVP_TJDS_DETERMINISTIC): exact -- every bit of every product reaches the accumulators; y is the correctly
+//            rounded row sum.
+// WORDS = 1 (SMVP_TJDS_DETERMINISTIC_FAST): only the high word, scaled to 2^(T - 62): a product loses the bits below 2^-62
+//            of its row's bound (2^-9 of what one fp64 addition at that magnitude rounds away); the sum of the integers
+//            is still associative, so the result is just as reproducible; one 8-byte reduction and one conversion per
+//            run instead of two, half the accumulator traffic.  The bound is normwise (see smvp_cuda.h).
+// Tried and dropped (profiles/r02_logs/r02_tjds_sweep4.log): prefetch.global.L2 of the next round (3.62 -> 3.87 ms),
+// ld.global.nc.L1::no_allocate streams (3.62 -> 3.75 ms), 5 or 7 CTAs per SM (4.1 / 3.9 ms), 3-deep rounds at 8 CTAs (4.0 ms).
 constexpr int TJDS_MAX_UNROLL = 8;
-template <int UNROLL, bool SKEW, bool FAST, int MINB>
+template <int UNROLL, bool SKEW, bool FAST, int MINB, int WORDS>
 __global__ void __launch_bounds__(256, MINB) tjds_det_kernel(const int2 *__restrict__ blocks, const int32_t *__restrict__ start_pos,
                                                        const int32_t *__restrict__ row_ind, const double *__restrict__ val,
                                                        const double *__restrict__ x_perm, const int32_t *__restrict__ row_exp,
@@ -414,9 +422,10 @@ __global__ void __launch_bounds__(256, MINB) tjds_det_kernel(const int2 *__restr
     auto flush = [&]() {
         if (hi_acc != 0)
             atomicAdd(acc + acc_row, (unsigned long long)hi_acc); // hi words [0, rows), lo words [rows, 2 rows):
-        if (lo_acc != 0)
+        if (WORDS == 2 && lo_acc != 0)
             atomicAdd(acc + (int64_t)rows + acc_row, (unsigned long long)lo_acc); // a warp's reductions stay contiguous
     };
+    constexpr int FRAC = WORDS == 2 ? TJDS_FRAC : TJDS_FRAC - TJDS_W; // scale of the word(s) kept
     for (int32_t i0 = 0; i0 < nd; i0 += UNROLL)
     {
         int32_t r[UNROLL];
@@ -447,14 +456,19 @@ __global__ void __launch_bounds__(256, MINB) tjds_det_kernel(const int2 *__restr
                         flush();
                     acc_row = r[u];
                     hi_acc = lo_acc = 0;
-                    S = pow2_f64(TJDS_FRAC - (__ldg(row_exp + acc_row) + ex));
+                    S = pow2_f64(FRAC - (__ldg(row_exp + acc_row) + ex));
                 }
                 if (r[u] < 0)
                     p = 0.0; // dead slot: adds nothing to the current run
-                long long hi, lo;
-                fixed_split_fast(p, S, &hi, &lo);
-                hi_acc += hi;
-                lo_acc += lo;
+                if (WORDS == 2)
+                {
+                    long long hi, lo;
+                    fixed_split_fast(p, S, &hi, &lo);
+                    hi_acc += hi;
+                    lo_acc += lo;
+                }
+                else
+                    hi_acc += __double2ll_rz(__dmul_rn(p, S)); // == the high word of the two-word split
             }
             else if (r[u] >= 0 && p != 0.0)
             {
@@ -473,7 +487,8 @@ __global__ void __launch_bounds__(256, MINB) tjds_det_kernel(const int2 *__restr
                 else
                     fixed_split(p, T, &hi, &lo);
                 hi_acc += hi;
-                lo_acc += lo;
+                if (WORDS == 2)
+                    lo_acc += lo;
             }
         }
     }
@@ -484,7 +499,7 @@ __global__ void __launch_bounds__(256, MINB) tjds_det_kernel(const int2 *__restr
 // row_rank != NULL: the accumulators and row_exp are in popularity-rank order (relabelled handle), y is not
 __global__ void __launch_bounds__(256) tjds_det_finalize_kernel(const long long *__restrict__ acc, const int32_t *__restrict__ row_exp,
                                                                 const int32_t *__restrict__ x_exp, int32_t rows, double *__restrict__ y,
-                                                                const int32_t *__restrict__ row_rank)
+                                                                const int32_t *__restrict__ row_rank, int words)
 {
     const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows)
@@ -492,7 +507,7 @@ __global__ void __launch_bounds__(256) tjds_det_finalize_kernel(const long long 
     const int32_t r = row_rank ? row_rank[row] : row;
     longlong2 a;
     a.x = acc[r];
-    a.y = acc[(int64_t)rows + r];
+    a.y = words == 2 ? acc[(int64_t)rows + r] : 0; // one word: the value is hi * 2^(T - 62), i.e. lo = 0 below
     double out = 0.0;
     if (a.x != 0 || a.y != 0)
     {
@@ -648,7 +663,7 @@ static int tjds_det_route(smvp_tjds *A)
         // and no visited row without an exponent (all-zero rows), and an x that is not all zero
         const int32_t lo_r = A->det_flags[2];
         A->det_fast = (ok && !(A->det_flags[0] & 2) && ex != EXP_NONE && er != EXP_NONE && lo_r != EXP_LOW_NONE &&
-                       (int64_t)lo_r + ex >= TJDS_FRAC - 1023 && (int64_t)er + ex <= TJDS_FRAC + 1022 &&
+                       (int64_t)lo_r + ex >= TJDS_FRAC - 1023 && (int64_t)er + ex <= TJDS_FRAC - TJDS_W + 1022 &&
                        getenv("SMVP_TJDS_DET_GENERAL") == nullptr)
                           ? 1
                           : -1;
@@ -708,7 +723,7 @@ static int tjds_prepare(smvp_tjds *A, int variant, cudaStream_t s)
         return SMVP_E_ARG; // smvp_tjds_set_x_device has not been called
     SMVP_TRY(tjds_plan(A, s));
     SMVP_TRY(tjds_relabel_plan(A, s));
-    if (variant == SMVP_TJDS_DETERMINISTIC)
+    if (variant != SMVP_TJDS_ATOMIC)
     {
         SMVP_TRY(tjds_prepare_det(A, s));
         SMVP_TRY(tjds_det_route(A));
@@ -747,40 +762,45 @@ static int tjds_pass(smvp_tjds *A, double *d_y, int variant, int32_t diag_limit,
     }
     else
     {
-        SMVP_CUDA(cudaMemsetAsync(A->acc, 0, sizeof(long long) * 2 * (size_t)A->rows, s));
+        const int words = variant == SMVP_TJDS_DETERMINISTIC_FAST ? 1 : 2;
+        SMVP_CUDA(cudaMemsetAsync(A->acc, 0, sizeof(long long) * (size_t)words * (size_t)A->rows, s));
         if (blocks > 0 && lim > 0)
         {
-#define SMVP_DET_LAUNCH(U, SK, FA, MB)                                                                                    \
-    SMVP_LAUNCH((tjds_det_kernel<U, SK, FA, MB>), blocks, 256, 0, s, SMVP_TJDS_ARGS_COMMON, (const int32_t *)A->row_exp, \
-                (const int32_t *)A->x_exp, (unsigned long long *)A->acc, A->rows, A->nslots, lim)
+#define SMVP_DET_LAUNCH(U, SK, FA, MB, MB1)                                                                                       \
+    do                                                                                                                            \
+    {                                                                                                                             \
+        if (words == 2)                                                                                                           \
+            SMVP_LAUNCH((tjds_det_kernel<U, SK, FA, MB, 2>), blocks, 256, 0, s, SMVP_TJDS_ARGS_COMMON, (const int32_t *)A->row_exp, \
+                        (const int32_t *)A->x_exp, (unsigned long long *)A->acc, A->rows, A->nslots, lim);                         \
+        else                                                                                                                      \
+            SMVP_LAUNCH((tjds_det_kernel<U, SK, FA, MB1, 1>), blocks, 256, 0, s, SMVP_TJDS_ARGS_COMMON, (const int32_t *)A->row_exp, \
+                        (const int32_t *)A->x_exp, (unsigned long long *)A->acc, A->rows, A->nslots, lim);                         \
+    } while (0)
             const char *ce = getenv("SMVP_TJDS_DET_CFG"); // tuning hook
             const int cfg = ce && ce[0] ? atoi(ce) : 0;
             const bool fast = A->det_fast == 1;
+            // CTAs per SM: 6 for the two-word kernel (40 registers).  The one-word kernel runs at 8 (32 registers, at the
+            // price of ONE 4-byte spill outside the loop): 3.0 - 3.1 ms against 3.85 ms at 6 CTAs without the spill
+            // (profiles/r02_logs/r02_tjds_sweep5.log) -- the kernel is latency-bound, residency wins.
             if (skew && fast)
             {
                 if (cfg == 1)
-                    SMVP_DET_LAUNCH(3, true, true, 8);
+                    SMVP_DET_LAUNCH(3, true, true, 8, 8);
                 else if (cfg == 2)
-                    SMVP_DET_LAUNCH(2, true, true, 8);
-                else if (cfg == 3)
-                    SMVP_DET_LAUNCH(8, true, true, 3);
-                else if (cfg == 4)
-                    SMVP_DET_LAUNCH(6, true, true, 4);
-                else if (cfg == 5)
-                    SMVP_DET_LAUNCH(4, true, true, 5);
+                    SMVP_DET_LAUNCH(4, true, true, 6, 6);
                 else
-                    SMVP_DET_LAUNCH(4, true, true, 6);
+                    SMVP_DET_LAUNCH(4, true, true, 6, 8);
             }
             else if (skew)
-                SMVP_DET_LAUNCH(4, true, false, 6);
+                SMVP_DET_LAUNCH(4, true, false, 6, 6);
             else if (fast)
-                SMVP_DET_LAUNCH(4, false, true, 6);
+                SMVP_DET_LAUNCH(4, false, true, 6, 6);
             else
-                SMVP_DET_LAUNCH(4, false, false, 6);
+                SMVP_DET_LAUNCH(4, false, false, 6, 6);
         }
         SMVP_LAUNCH(tjds_det_finalize_kernel, (unsigned)ceil_div64(A->rows, 256), 256, 0, s, (const long long *)A->acc,
                     (const int32_t *)A->row_exp, (const int32_t *)A->x_exp, A->rows, d_y,
-                    ranked ? (const int32_t *)A->row_rank : nullptr);
+                    ranked ? (const int32_t *)A->row_rank : nullptr, words);
     }
     SMVP_CUDA(cudaGetLastError());
     return SMVP_OK;
@@ -790,7 +810,7 @@ extern "C" int smvp_tjds_mult_device(smvp_tjds *A, double *d_y, int variant, int
 {
     if (!A || (A->rows > 0 && !d_y))
         return SMVP_E_ARG;
-    if (variant != SMVP_TJDS_ATOMIC && variant != SMVP_TJDS_DETERMINISTIC)
+    if (variant != SMVP_TJDS_ATOMIC && variant != SMVP_TJDS_DETERMINISTIC && variant != SMVP_TJDS_DETERMINISTIC_FAST)
         return SMVP_E_ARG;
     if (A->rows == 0)
         return SMVP_OK;
@@ -804,7 +824,7 @@ extern "C" int smvp_tjds_mult(smvp_tjds *A, const double *x_host, double *y_host
 {
     if (!A || iters < 1 || (A->cols > 0 && !x_host) || (A->rows > 0 && !y_host))
         return SMVP_E_ARG;
-    if (variant != SMVP_TJDS_ATOMIC && variant != SMVP_TJDS_DETERMINISTIC)
+    if (variant != SMVP_TJDS_ATOMIC && variant != SMVP_TJDS_DETERMINISTIC && variant != SMVP_TJDS_DETERMINISTIC_FAST)
         return SMVP_E_ARG;
     if (!A->d_x)
         SMVP_CUDA(dev_alloc(&A->d_x, A->cols));
@@ -853,6 +873,7 @@ extern "C" int smvp_tjds_info(const smvp_tjds *A, smvp_tjds_info_t *out)
     out->device_bytes = A->device_bytes;
     out->launches_per_mult[SMVP_TJDS_ATOMIC] = A->relabel_state == 1 ? 2 : 1;
     out->launches_per_mult[SMVP_TJDS_DETERMINISTIC] = 2;
+    out->launches_per_mult[SMVP_TJDS_DETERMINISTIC_FAST] = 2;
     out->y_relabel = A->relabel_state;
     out->skewed_walk = A->skew;
     out->det_route = A->det_route;

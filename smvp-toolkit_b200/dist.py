@@ -740,7 +740,7 @@ class ColBlockTjds:
         # so the bits do not depend on NCCL's reduction order (SMVP_TJDS_ORDERED=0/1 forces it off/on for either variant)
         forced = os.environ.get("SMVP_TJDS_ORDERED")
         self.ordered = world > 1 and exchange == "nccl" and (
-            forced == "1" or (forced != "0" and variant == eng.TJDS_DETERMINISTIC))
+            forced == "1" or (forced != "0" and variant != eng.TJDS_ATOMIC))
         self.scratch, self.symm, self.part_ptrs = None, None, None
         if self.ordered:
             # the partial y lives in symmetric memory: the owner of a row block pulls that block from every rank over
@@ -762,7 +762,8 @@ class ColBlockTjds:
             if self.symm is None:
                 self.scratch = torch.empty(self.Mp, dtype=torch.float64, device="cuda")
         self.local_rows_out = self.Mp // world
-        self.variant_name = {eng.TJDS_ATOMIC: "atomic", eng.TJDS_DETERMINISTIC: "deterministic"}[variant]
+        self.variant_name = {eng.TJDS_ATOMIC: "atomic", eng.TJDS_DETERMINISTIC: "deterministic",
+                             eng.TJDS_DETERMINISTIC_FAST: "deterministic_fast"}[variant]
         self.kernel_name = "tjds_%s_kernel" % ("atomic" if variant == eng.TJDS_ATOMIC else "det")
         self.partition_desc = ("column blocks balanced by nnz, %d ranks; x sliced; partial y %s" %
                                (world, (("pulled block-wise over NVLink peer mappings" if self.symm is not None else

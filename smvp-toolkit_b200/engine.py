@@ -25,7 +25,7 @@ LIB_PATH = os.environ.get("SMVP_LIB_PATH") or os.path.join(HERE, "lib", "libsmvp
 COO_DT = np.dtype([("row", "<i4"), ("col", "<i4"), ("val", "<f8")])
 
 CSR_AUTO, CSR_VECTOR, CSR_MERGE = 0, 1, 2
-TJDS_ATOMIC, TJDS_DETERMINISTIC = 0, 1
+TJDS_ATOMIC, TJDS_DETERMINISTIC, TJDS_DETERMINISTIC_FAST = 0, 1, 2
 VAL_STENCIL, VAL_HASH, VAL_ONES = 0, 1, 2
 
 OK, E_ARG, E_ALLOC, E_CUDA, E_RANGE, E_TOOBIG = 0, -1, -2, -3, -4, -5
@@ -50,7 +50,7 @@ class _CsrInfo(ctypes.Structure):
 class _TjdsInfo(ctypes.Structure):
     _fields_ = [("rows", ctypes.c_int32), ("cols", ctypes.c_int32), ("nnz", ctypes.c_int64), ("ndiag", ctypes.c_int32),
                 ("ref_diag_limit", ctypes.c_int32), ("input_order", ctypes.c_int32), ("bytes_per_mult", ctypes.c_int64),
-                ("device_bytes", ctypes.c_int64), ("launches_per_mult", ctypes.c_int32 * 2), ("y_relabel", ctypes.c_int32),
+                ("device_bytes", ctypes.c_int64), ("launches_per_mult", ctypes.c_int32 * 3), ("y_relabel", ctypes.c_int32),
                 ("skewed_walk", ctypes.c_int32), ("det_route", ctypes.c_int32)]
 
 

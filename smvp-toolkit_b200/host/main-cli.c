@@ -14,7 +14,7 @@
  *   <file>                Matrix Market file; options come BEFORE it (POSIXLY_CORRECT parsing, as popt's
  *                         POPT_CONTEXT_POSIXMEHARDER at main-cli.c:1254)
  * Additions (long options only, so no reference option changes meaning):
- *   --csr-variant=auto|vector|merge      --tjds-variant=atomic|deterministic
+ *   --csr-variant=auto|vector|merge      --tjds-variant=atomic|deterministic|fast
  *   --ref-compat          TJDS walks only the diagonals the SHIPPED reference loop walks (main-cli.c:865,
  *                         :1013), reproducing its golden TJDS reports; default is the full product
  *   --json                print one machine-readable line per algorithm (GB/s, GFLOP/s, variant)
@@ -62,7 +62,7 @@ static void usage(const char *argv0)
     fprintf(stderr,
             "Usage: %s [-acgt?] [-a|--all-algs] [-c|--csr] [-g|--cisr-gen] [-t|--tjds] [-n|--number=1000]\n"
             "        [-s|--slots=16] [-d|--dir=./] [--csr-variant=auto|vector|merge]\n"
-            "        [--tjds-variant=atomic|deterministic] [--ref-compat] [--json] [--expand-symmetric] [-?|--help] [--usage] [OPTIONS] <file>\n",
+            "        [--tjds-variant=atomic|deterministic|fast] [--ref-compat] [--json] [--expand-symmetric] [-?|--help] [--usage] [OPTIONS] <file>\n",
             argv0);
 }
 
@@ -168,8 +168,10 @@ int main(int argc, char *argv[])
                 tjds_variant = SMVP_TJDS_ATOMIC;
             else if (strcmp(optarg, "deterministic") == 0)
                 tjds_variant = SMVP_TJDS_DETERMINISTIC;
+            else if (strcmp(optarg, "fast") == 0)
+                tjds_variant = SMVP_TJDS_DETERMINISTIC_FAST;
             else
-                die("Unknown --tjds-variant (atomic, deterministic).");
+                die("Unknown --tjds-variant (atomic, deterministic, fast).");
             break;
         case 1003:
             ref_compat = 1;
@@ -278,7 +280,7 @@ int main(int argc, char *argv[])
         if (json)
             printf("{\"alg\": \"TJDS\", \"variant\": \"%s\", \"rows\": %d, \"cols\": %d, \"nnz\": %lld, \"ndiag\": %d, \"iters\": %d, "
                    "\"avg_ms\": %.9g, \"min_ms\": %.9g, \"gbps\": %.6g, \"gflops\": %.6g, \"ref_compat\": %d}\n",
-                   tjds_variant == SMVP_TJDS_ATOMIC ? "atomic" : "deterministic", rows, cols, (long long)nnz, info.ndiag, calc_iter,
+                   tjds_variant == SMVP_TJDS_ATOMIC ? "atomic" : (tjds_variant == SMVP_TJDS_DETERMINISTIC ? "deterministic" : "deterministic_fast"), rows, cols, (long long)nnz, info.ndiag, calc_iter,
                    st.time_avg, st.time_min, info.bytes_per_mult / (st.time_avg * 1e6), 2.0 * nnz / (st.time_avg * 1e6), ref_compat);
         smvp_tjds_free(T);
     }

@@ -58,15 +58,19 @@ def test_library_is_sm100a_with_tma(eng):
 
 def test_hot_kernels_do_not_spill(eng):
     """A register spill in the multiply kernels halves their throughput (measured, profiles/): the build must
-    stay spill-free (STACK:0) for every CSR / TJDS multiply kernel."""
+    stay spill-free (STACK:0) for every CSR / TJDS multiply kernel.  One deliberate exception, decided by measurement
+    (profiles/r02_logs/r02_tjds_sweep5.log): the one-word deterministic TJDS kernel is forced to 32 registers for 8 CTAs per
+    SM and keeps ONE 4-byte value on the stack (3.0 - 3.1 ms against 3.85 ms spill-free at 6 CTAs per SM)."""
     out = subprocess.run(["cuobjdump", "-res-usage", eng.LIB_PATH], capture_output=True, text=True).stdout
     lines = out.splitlines()
     seen = 0
+    allowed = {"tjds_det_kernelILi4ELb1ELb1ELi8ELi1E": 8}  # <UNROLL 4, skewed, fast split, 8 CTAs/SM, one word>
     for i, ln in enumerate(lines):
         if "Function" in ln and re.search(r"csr_merge_warp_kernel|csr_vector_kernel|tjds_atomic_kernel|tjds_det_kernel", ln):
             usage = lines[i + 1]
             m = re.search(r"STACK:(\d+)", usage)
-            assert m and int(m.group(1)) == 0, (ln, usage)
+            limit = max([v for k, v in allowed.items() if k in ln] + [0])
+            assert m and int(m.group(1)) <= limit, (ln, usage)
             seen += 1
     assert seen >= 4
 

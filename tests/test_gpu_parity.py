@@ -62,12 +62,13 @@ def check_tjds(eng, coo, m, n, x, y_csr):
     assert A.ref_diag_limit == t.ref_limit
     y_ref = oracle.tjds_mult(t, x)
     ya, _ = A.mult(x, iters=2, variant=eng.TJDS_ATOMIC)
-    yd1, _ = A.mult(x, iters=1, variant=eng.TJDS_DETERMINISTIC)
-    yd2, _ = A.mult(x, iters=3, variant=eng.TJDS_DETERMINISTIC)
     assert util.rel_l2(ya, y_ref) <= TOL
-    assert util.rel_l2(yd1, y_ref) <= TOL
-    assert util.rel_l2(ya, y_csr) <= TOL and util.rel_l2(yd1, y_csr) <= TOL  # TJDS == CSR, pins x indexing
-    assert np.array_equal(yd1.view(np.int64), yd2.view(np.int64)), "deterministic variant differs run to run"
+    assert util.rel_l2(ya, y_csr) <= TOL  # TJDS == CSR, pins x indexing
+    for det in (eng.TJDS_DETERMINISTIC_FAST, eng.TJDS_DETERMINISTIC):  # one-word and two-word (exact) integer accumulation
+        yd1, _ = A.mult(x, iters=1, variant=det)
+        yd2, _ = A.mult(x, iters=3, variant=det)
+        assert util.rel_l2(yd1, y_ref) <= TOL and util.rel_l2(yd1, y_csr) <= TOL
+        assert np.array_equal(yd1.view(np.int64), yd2.view(np.int64)), "deterministic variant differs run to run"
     A.free()
     return yd1
 
@@ -181,7 +182,8 @@ def test_out_of_range_and_bad_args(eng):
 
 
 def test_deterministic_tjds_is_exactly_rounded(eng):
-    """The fixed-point accumulation is exact: every y_r equals the correctly rounded sum of the fp64 products."""
+    """SMVP_TJDS_DETERMINISTIC: the two-word fixed-point accumulation is exact, every y_r equals the correctly rounded sum of
+    the fp64 products.  SMVP_TJDS_DETERMINISTIC_FAST (one word): within its documented normwise bound."""
     rng = np.random.default_rng(5)
     m, n, nnz = 400, 400, 20000
     coo = util.random_coo(rng, m, n, nnz)
@@ -189,12 +191,20 @@ def test_deterministic_tjds_is_exactly_rounded(eng):
     x = rng.uniform(-1, 1, n) * 10.0 ** rng.integers(-3, 3, n)
     A = eng.TjdsMatrix.build(coo, m, n)
     y, _ = A.mult(x, 1, eng.TJDS_DETERMINISTIC)
+    y1, _ = A.mult(x, 1, eng.TJDS_DETERMINISTIC_FAST)
     exact = np.zeros(m)
     for r in range(m):
         sel = coo["row"] == r
         exact[r] = math.fsum((coo["val"][sel] * x[coo["col"][sel]]).tolist())
     ulp = np.spacing(np.abs(exact))
     assert np.all(np.abs(y - exact) <= 2 * ulp + 1e-300)
+    # the one-word variant truncates each product at 2^-62 of its row's bound B_r >= max|a_rj| * max|x| * count_r (a power
+    # of two, at most 8x that product): the documented NORMWISE bound, checked here with x spanning six decades
+    amax, cnt = np.zeros(m), np.zeros(m)
+    np.maximum.at(amax, coo["row"], np.abs(coo["val"]))
+    np.add.at(cnt, coo["row"], 1.0)
+    bound = cnt * 2.0 ** -62 * (8.0 * amax * np.abs(x).max() * np.maximum(cnt, 1.0))
+    assert np.all(np.abs(y1 - exact) <= bound + np.spacing(np.abs(exact)) + 1e-300)
     A.free()
 
 

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--modes", default="0,1")
     ap.add_argument("--hints", default="off,8192x4194304,0x4194304,8192x0,65536x8388608")
     ap.add_argument("--no-vector", action="store_true")
+    ap.add_argument("--persist", default="0", help="comma list of SMVP_L2_PERSIST_MB values tried with every hint setting")
     args = ap.parse_args()
     src = sdist.RmatSource(eng, args.scale, args.edge_factor << args.scale)
     M = N = src.rows
@@ -61,7 +62,9 @@ def main():
                 os.environ["SMVP_RANKED_HINTS"] = "1"
                 os.environ["SMVP_HOT_L1"], os.environ["SMVP_HOT_L2"] = hint.split("x")
             for cfg in [int(t) for t in args.cfgs.split(",")]:
+              for pmb in (args.persist.split(",") if mode != "0" else ["0"]):
                 os.environ["SMVP_MERGE_CFG"] = str(cfg)
+                os.environ["SMVP_L2_PERSIST_MB"] = pmb
                 y.fill_(float("nan"))
                 ms = timeit(lambda: A.mult_device(None, y, eng.CSR_MERGE), args.steps)
                 tag = ""
@@ -69,7 +72,9 @@ def main():
                     y_plain[cfg] = y.clone()
                 elif cfg in y_plain:
                     tag = "bit-identical" if torch.equal(y, y_plain[cfg]) else "DIFFERS from plain"
-                print("  hints %-16s merge cfg %d: %8.3f ms  %8.1f GB/s  %s" % (hint, cfg, ms, nbytes / ms / 1e6, tag), flush=True)
+                print("  hints %-16s persist %3s MB merge cfg %d: %8.3f ms  %8.1f GB/s  %s" % (hint, pmb, cfg, ms, nbytes / ms / 1e6, tag),
+                      flush=True)
+        os.environ.pop("SMVP_L2_PERSIST_MB", None)
         for k in ("SMVP_MERGE_CFG", "SMVP_RANKED_HINTS", "SMVP_HOT_L1", "SMVP_HOT_L2"):
             os.environ.pop(k, None)
         if not args.no_vector:
