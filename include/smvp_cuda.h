@@ -156,6 +156,11 @@ typedef struct smvp_csr_info_t
     int32_t x_relabel;        /* multiply plan: 1 = the kernels read popularity-relabelled column indices
                                  and a permuted copy of x (row sums keep their order: y is bit-identical),
                                  -1 = natural order kept, 0 = not decided yet (decided at the first pass) */
+    int32_t x_split;          /* multiply plan of a relabelled handle: 1 = the merge-path multiply runs in two passes, the
+                                 entries whose column is among the 4 Mi most popular (their part of x stays in L2) and
+                                 the others (y += ...): a row sum is then taken in two parts -- within 1e-12, not
+                                 bit-identical to the one-pass order; -1 = one pass (the default: the split is an
+                                 opt-in experiment, SMVP_CSR_SPLIT=1, that loses on R-MAT); 0 = not decided yet   */
 } smvp_csr_info_t;
 
 typedef struct smvp_tjds_info_t

@@ -170,6 +170,12 @@ struct smvp_csr
     int32_t *x_order;    // [cols] column with rank p
     double *x_rel;       // [cols] x in rank order
     const double *x_set; // the x last given to smvp_csr_set_x_device (caller-owned)
+    // hot / cold split of a relabelled handle (relabel.cu): two CSR matrices over the SAME rank-ordered column space,
+    // `hot` holding the entries whose column rank is below the L2-resident prefix of x_rel, `cold` the others.  The
+    // merge-path multiply runs hot (every gather an L2 hit) then cold (+=).  0 undecided, 1 in use, -1 not used.
+    int32_t split_state;
+    int32_t ranked_cols; // 1: col_ind already holds popularity ranks (a hot / cold part): the ranked gather hints apply
+    smvp_csr *hot, *cold;
 };
 namespace smvp
 {
@@ -177,6 +183,10 @@ void csr_pipe_release(smvp_csr *A);                                // csr_mult.c
 int csr_relabel_plan(smvp_csr *A, cudaStream_t s);                 // relabel.cu
 int csr_relabel_x(smvp_csr *A, const double *d_x, cudaStream_t s); // relabel.cu
 void csr_relabel_release(smvp_csr *A);                             // relabel.cu
+int csr_split_plan(smvp_csr *A, cudaStream_t s);                   // relabel.cu: after csr_relabel_plan
+void csr_release(smvp_csr *A);                                     // csr_build.cu
+int csr_build_impl(const int32_t *d_row, const int32_t *d_col, const double *d_val, int32_t rows, int32_t cols, int64_t nnz,
+                   smvp_csr *A, cudaStream_t s);                   // csr_build.cu
 } // namespace smvp
 
 struct smvp_tjds

@@ -25,10 +25,12 @@ __global__ void __launch_bounds__(256) gather_csr_kernel(const uint32_t *__restr
 
 __global__ void set_last_kernel(int32_t *row_ptr, int32_t rows, int32_t nnz) { row_ptr[rows] = nnz; }
 
-static void csr_release(smvp_csr *A)
+void csr_release(smvp_csr *A)
 {
     if (!A)
         return;
+    csr_release(A->hot);
+    csr_release(A->cold);
     cudaFree(A->row_ptr);
     cudaFree(A->col_ind);
     cudaFree(A->val);
@@ -42,7 +44,7 @@ static void csr_release(smvp_csr *A)
     delete A;
 }
 
-static int csr_build_impl(const int32_t *d_row, const int32_t *d_col, const double *d_val, int32_t rows, int32_t cols,
+int csr_build_impl(const int32_t *d_row, const int32_t *d_col, const double *d_val, int32_t rows, int32_t cols,
                           int64_t nnz, smvp_csr *A, cudaStream_t s)
 {
     int order = ORDER_ROW_COL;

@@ -181,6 +181,19 @@ struct YFan
     double *p[SMVP_MAX_FANOUT];
     int n;
 };
+// accum != 0 (second pass of a hot / cold split, never with a fan-out): y[row] += v.  Every row has exactly one writer in
+// a pass (the lane that ends it, or the fix-up kernel for rows cut by tile boundaries), so the read-modify-write is safe.
+template <bool FANOUT>
+__device__ __forceinline__ void store_y_acc(double *__restrict__ y, const YFan &fan, int64_t row, double v, int32_t accum)
+{
+    if (FANOUT)
+    {
+        for (int k = 0; k < fan.n; k++)
+            fan.p[k][row] = v;
+    }
+    else
+        y[row] = accum ? __dadd_rn(y[row], v) : v;
+}
 template <bool FANOUT>
 __device__ __forceinline__ void store_y(double *__restrict__ y, const YFan &fan, int64_t row, double v)
 {
@@ -419,7 +432,8 @@ __device__ __forceinline__ TileView make_tile(int32_t r0, int32_t r1, int32_t t,
 // of the tile where it ends).  tile_row[u+1] is the row tile u's carry belongs to.
 template <bool FANOUT>
 __device__ __forceinline__ void merge_fixup_tile(int32_t t, const int32_t *__restrict__ tile_row, const double *__restrict__ head_val,
-                                                 const double *__restrict__ carry_val, double *__restrict__ y, const YFan &fan)
+                                                 const double *__restrict__ carry_val, double *__restrict__ y, const YFan &fan,
+                                                 int32_t accum)
 {
     // everything the common case needs is loaded up front (independent loads: one memory round trip)
     const int32_t r = tile_row[t];
@@ -446,7 +460,7 @@ __device__ __forceinline__ void merge_fixup_tile(int32_t t, const int32_t *__res
             acc = __dadd_rn(acc, __ldcg(carry_val + k));
         acc = __dadd_rn(acc, h);
     }
-    store_y<FANOUT>(y, fan, r, acc);
+    store_y_acc<FANOUT>(y, fan, r, acc, accum);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -461,7 +475,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                           const double *__restrict__ x, double *__restrict__ y, const int32_t *__restrict__ tile_row, int32_t rows,
                           int64_t nnz, int32_t tile_begin, int32_t num_tiles, double *__restrict__ head_val,
                           double *__restrict__ carry_val, const __grid_constant__ YFan fan, int32_t hot_l1, int32_t hot_l2,
-                          int32_t early_dependents)
+                          int32_t early_dependents, int32_t accum)
 {
     // Small grids (early_dependents != 0): let the fix-up kernel, launched with programmatic stream serialization, be
     // scheduled NOW; it parks at griddepcontrol.wait until this grid has completed and flushed.  In the batched `-n` loop
@@ -663,7 +677,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                             first_sum = sum;
                         }
                         else
-                            store_y<FANOUT>(y, fan, (int64_t)tile_r0 + row, sum);
+                            store_y_acc<FANOUT>(y, fan, (int64_t)tile_r0 + row, sum, accum);
                         sum = 0.0;
                         row++;
                         until = (row < i_next ? row_end(row) : 0x7fffffff) - j0;
@@ -681,7 +695,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                     first_sum = sum;
                 }
                 else
-                    store_y<FANOUT>(y, fan, (int64_t)tile_r0 + row, sum);
+                    store_y_acc<FANOUT>(y, fan, (int64_t)tile_r0 + row, sum, accum);
                 sum = 0.0;
                 row++;
             }
@@ -727,7 +741,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             if (i0 == 0)
                 head_val[t] = first_sum;
             else
-                store_y<FANOUT>(y, fan, (int64_t)tile_r0 + i0, first_sum);
+                store_y_acc<FANOUT>(y, fan, (int64_t)tile_r0 + i0, first_sum, accum);
         }
         if (lane == 31)
             carry_val[t] = scan; // partial of the row that continues into the next tile
@@ -741,13 +755,13 @@ template <bool FANOUT>
 __global__ void __launch_bounds__(256) merge_fixup_kernel(const int32_t *__restrict__ tile_row, const double *__restrict__ head_val,
                                                           const double *__restrict__ carry_val, int32_t tile_begin,
                                                           int32_t num_tiles, double *__restrict__ y,
-                                                          const __grid_constant__ YFan fan)
+                                                          const __grid_constant__ YFan fan, int32_t accum)
 {
     // no-op unless launched with programmatic stream serialization: then it waits here for the merge kernel's results
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int32_t t = tile_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (t < num_tiles)
-        merge_fixup_tile<FANOUT>(t, tile_row, head_val, carry_val, y, fan);
+        merge_fixup_tile<FANOUT>(t, tile_row, head_val, carry_val, y, fan, accum);
 }
 
 // ---- the instantiations AUTO chooses from: {warps per CTA, items per thread, stages per warp, min CTAs/SM}.
@@ -820,7 +834,7 @@ static void hot_limits(int32_t *l1, int32_t *l2)
 
 template <int WARPS, int IPT, int STAGES, int MINB, bool FANOUT, bool RANKED, bool UNI>
 static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, const YFan *fanp, cudaStream_t s, int32_t tile_begin,
-                         int32_t tile_end)
+                         int32_t tile_end, int32_t accum)
 {
     using Shape = MergeShape<32, IPT, STAGES>;
     constexpr int SMEM = WARPS * Shape::SMEM_BYTES;
@@ -865,7 +879,7 @@ static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, cons
             pdl_ok = getenv("SMVP_NO_PDL") == nullptr ? 1 : 0;
         const bool early = pdl_ok == 1 && ntiles <= MERGE_PDL_TILES;
         SMVP_LAUNCH(kern, (unsigned)grid, WARPS * 32, SMEM, s, A->row_ptr, mult_cols(A), A->val, d_x, d_y, A->tile_row, A->rows,
-                    A->nnz, tile_begin, tile_end, A->head_val, A->carry_val, fan, hot_l1, hot_l2, early ? 1 : 0);
+                    A->nnz, tile_begin, tile_end, A->head_val, A->carry_val, fan, hot_l1, hot_l2, early ? 1 : 0, accum);
         if (early)
         {
             cudaLaunchConfig_t cfg = {};
@@ -879,12 +893,12 @@ static int launch_wmerge(const smvp_csr *A, const double *d_x, double *d_y, cons
             cfg.attrs = attr;
             cfg.numAttrs = 1;
             SMVP_CUDA(cudaLaunchKernelEx(&cfg, merge_fixup_kernel<FANOUT>, (const int32_t *)A->tile_row, (const double *)A->head_val,
-                                         (const double *)A->carry_val, tile_begin, tile_end, d_y, fan));
+                                         (const double *)A->carry_val, tile_begin, tile_end, d_y, fan, accum));
             ::smvp::g_launches.fetch_add(1, std::memory_order_relaxed);
         }
         else
             SMVP_LAUNCH(merge_fixup_kernel<FANOUT>, (unsigned)ceil_div64(ntiles, 256), 256, 0, s, (const int32_t *)A->tile_row,
-                        (const double *)A->head_val, (const double *)A->carry_val, tile_begin, tile_end, d_y, fan);
+                        (const double *)A->head_val, (const double *)A->carry_val, tile_begin, tile_end, d_y, fan, accum);
     }
     return SMVP_OK;
 }
@@ -905,24 +919,32 @@ static int wmerge_tile_items(int cfg)
 
 // tiles [tile_begin, tile_end) of the plan; (0, -1) = all
 static int csr_mult_merge(smvp_csr *A, const double *d_x, double *d_y, const YFan *fan, cudaStream_t s, int32_t tile_begin = 0,
-                          int32_t tile_end = -1)
+                          int32_t tile_end = -1, int32_t accum = 0)
 {
+    // hot / cold split (relabel.cu): whole passes without a fan-out run as y = hot * x_rel, then y += cold * x_rel
+    if (A->split_state == 1 && !fan && tile_begin == 0 && tile_end < 0 && !accum)
+    {
+        SMVP_TRY(csr_mult_merge(A->hot, d_x, d_y, nullptr, s, 0, -1, 0));
+        return csr_mult_merge(A->cold, d_x, d_y, nullptr, s, 0, -1, 1);
+    }
+    if (accum && fan)
+        return SMVP_E_ARG;
     const int cfg = pick_merge_cfg(A);
     SMVP_TRY(merge_plan(A, cfg, s));
     if (tile_end < 0)
         tile_end = A->merge_tiles;
     // a relabelled handle indexes x by popularity rank: the gathers carry cache-retention hints (SMVP_RANKED_HINTS=0: off)
     const char *rh = getenv("SMVP_RANKED_HINTS");
-    const bool ranked = A->relabel_state == 1 && !(rh && rh[0] == '0');
+    const bool ranked = (A->relabel_state == 1 || A->ranked_cols == 1) && !(rh && rh[0] == '0');
     switch (cfg)
     {
 #define X(id, wp, i, st, mb, un)                                                                                       \
     case id:                                                                                                           \
-        if (ranked)                                                                                                    \
-            return fan ? launch_wmerge<wp, i, st, mb, true, true, un>(A, d_x, d_y, fan, s, tile_begin, tile_end)       \
-                       : launch_wmerge<wp, i, st, mb, false, true, un>(A, d_x, d_y, nullptr, s, tile_begin, tile_end); \
-        return fan ? launch_wmerge<wp, i, st, mb, true, false, un>(A, d_x, d_y, fan, s, tile_begin, tile_end)          \
-                   : launch_wmerge<wp, i, st, mb, false, false, un>(A, d_x, d_y, nullptr, s, tile_begin, tile_end);
+        if (ranked)                                                                                                           \
+            return fan ? launch_wmerge<wp, i, st, mb, true, true, un>(A, d_x, d_y, fan, s, tile_begin, tile_end, accum)       \
+                       : launch_wmerge<wp, i, st, mb, false, true, un>(A, d_x, d_y, nullptr, s, tile_begin, tile_end, accum); \
+        return fan ? launch_wmerge<wp, i, st, mb, true, false, un>(A, d_x, d_y, fan, s, tile_begin, tile_end, accum)          \
+                   : launch_wmerge<wp, i, st, mb, false, false, un>(A, d_x, d_y, nullptr, s, tile_begin, tile_end, accum);
         SMVP_WMERGE_CFGS(X)
 #undef X
     default:
@@ -1504,5 +1526,8 @@ extern "C" int smvp_csr_info(const smvp_csr *A, smvp_csr_info_t *out)
     out->launches_per_mult[SMVP_CSR_MERGE] = 2;
     out->launches_per_mult[SMVP_CSR_AUTO] = out->launches_per_mult[out->auto_variant];
     out->x_relabel = A->relabel_state;
+    out->x_split = A->split_state;
+    out->launches_per_mult[SMVP_CSR_MERGE] = A->split_state == 1 ? 4 : 2;
+    out->launches_per_mult[SMVP_CSR_AUTO] = out->launches_per_mult[out->auto_variant];
     return SMVP_OK;
 }

@@ -652,7 +652,7 @@ def test_full_size_rmat_scale26(eng, monkeypatch):
     eng.synth_vector(d_x, n, 4242)
     x = d_x.cpu().numpy()
 
-    # ---- (b) full matrix, CSR: AUTO (relabelled at this size) vs natural order
+    # ---- (b) full matrix, CSR: AUTO (relabelled at this size), the opt-in hot / cold split, and the natural order
     A = eng.CsrMatrix.build_device(r, c, v, m, n, nnz)
     y_auto = torch.empty(m, dtype=torch.float64, device="cuda")
     A.set_x_device(d_x)
@@ -660,21 +660,31 @@ def test_full_size_rmat_scale26(eng, monkeypatch):
     torch.cuda.synchronize()
     if scale >= 26:
         assert A.x_relabel == 1, "AUTO is expected to relabel the column space of R-MAT scale 26"
+        assert A.x_split == -1, "the hot / cold split is opt-in (it loses on this matrix)"
     y_vec = torch.empty_like(y_auto)
     A.mult_device(None, y_vec, eng.CSR_VECTOR)
     torch.cuda.synchronize()
     assert float(torch.linalg.norm(y_vec - y_auto) / torch.linalg.norm(y_auto)) <= TOL
     A.free()
+    monkeypatch.setenv("SMVP_CSR_SPLIT", "1")
+    R = eng.CsrMatrix.build_device(r, c, v, m, n, nnz)
+    y_split = torch.empty_like(y_auto)
+    R.mult_device(d_x, y_split, eng.CSR_MERGE)
+    torch.cuda.synchronize()
+    assert scale < 26 or (R.x_relabel == 1 and R.x_split == 1)
+    R.free()
+    monkeypatch.delenv("SMVP_CSR_SPLIT")
     monkeypatch.setenv("SMVP_CSR_RELABEL", "0")
     P = eng.CsrMatrix.build_device(r, c, v, m, n, nnz)
     y_plain = torch.empty_like(y_auto)
     P.mult_device(d_x, y_plain, eng.CSR_MERGE)
     torch.cuda.synchronize()
-    assert P.x_relabel == -1
+    assert P.x_relabel == -1 and P.x_split == -1
     assert torch.equal(y_plain, y_auto), "relabelled and natural-order CSR must agree bit for bit"
+    assert float(torch.linalg.norm(y_split - y_plain) / torch.linalg.norm(y_plain)) <= TOL  # two-pass row sums
     P.free()
     monkeypatch.delenv("SMVP_CSR_RELABEL")
-    del y_vec, y_plain
+    del y_vec, y_plain, y_split
 
     # ---- (c) full matrix, TJDS
     T = eng.TjdsMatrix.build_device(r, c, v, m, n, nnz)
@@ -733,3 +743,137 @@ def test_full_size_rmat_scale26(eng, monkeypatch):
     S.free()
     for a in (br, bc, bv, r, c, v):
         a.free()
+
+
+# ---------------------------------------------------------------------------- the batched `-n` loop (round 2)
+@pytest.mark.parametrize("name", util.SAMPLES)
+def test_batched_n_loop_matches_single_pass(eng, monkeypatch, name):
+    """smvp_*_mult with many iterations on small matrices runs the loop batched (CUDA graphs; ONE looping CTA for the
+    tiny sample files; the merge fix-up launched early): y must equal the single exact pass -- bit for bit for CSR and
+    the deterministic TJDS variants, within 1e-12 for the atomic one -- for every variant, with batches that do and do
+    not divide the iteration count, and the per-iteration times must be positive and complete."""
+    m, n, coo = util.load_sample(name)
+    x = np.random.default_rng(11).uniform(-1, 1, n)
+    y_ref = oracle.csr_mult(*oracle.csr_build(coo, m, n), x)
+    A = eng.CsrMatrix.build(coo, m, n)
+    T = eng.TjdsMatrix.build(coo, m, n)
+    for variant in (eng.CSR_AUTO, eng.CSR_VECTOR, eng.CSR_MERGE):
+        y1, _ = A.mult(x, iters=1, variant=variant)
+        for iters in (4, 50, 123):
+            y, td = A.mult(x, iters=iters, variant=variant)
+            assert util.rel_l2(y, y_ref) <= TOL
+            if variant != eng.CSR_AUTO:  # AUTO may switch to the looping kernel (different lane layout, same tolerance)
+                assert np.array_equal(y.view(np.int64), y1.view(np.int64)), (variant, iters)
+            assert len(td.time_each) == iters and np.all(td.time_each > 0) and td.time_min > 0
+    for variant in (eng.TJDS_ATOMIC, eng.TJDS_DETERMINISTIC, eng.TJDS_DETERMINISTIC_FAST):
+        y1, _ = T.mult(x, iters=1, variant=variant)
+        for iters in (4, 77):
+            y, td = T.mult(x, iters=iters, variant=variant)
+            assert util.rel_l2(y, y_ref) <= TOL
+            if variant != eng.TJDS_ATOMIC:
+                assert np.array_equal(y.view(np.int64), y1.view(np.int64)), (variant, iters)
+            assert len(td.time_each) == iters and np.all(td.time_each > 0)
+    # reference-compatible diagonal limit through the batched loop
+    yl1, _ = T.mult(x, iters=1, variant=eng.TJDS_DETERMINISTIC, diag_limit=T.ref_diag_limit)
+    yl, _ = T.mult(x, iters=40, variant=eng.TJDS_DETERMINISTIC, diag_limit=T.ref_diag_limit)
+    assert np.array_equal(yl.view(np.int64), yl1.view(np.int64))
+    # the switches that turn the batching off give the same vector
+    monkeypatch.setenv("SMVP_EXACT_ITER_TIMES", "1")
+    y, td = A.mult(x, iters=20, variant=eng.CSR_AUTO)
+    assert util.rel_l2(y, y_ref) <= TOL and len(td.time_each) == 20
+    monkeypatch.delenv("SMVP_EXACT_ITER_TIMES")
+    monkeypatch.setenv("SMVP_NO_TINY_LOOP", "1")
+    monkeypatch.setenv("SMVP_NO_PDL", "1")
+    y, _ = A.mult(x, iters=20, variant=eng.CSR_AUTO)
+    assert util.rel_l2(y, y_ref) <= TOL
+    A.free()
+    T.free()
+
+
+def test_nonfinite_inputs_follow_ieee_propagation(eng):
+    """the loader accepts 'inf' / 'nan' (strtod).  The exact integer accumulation needs finite input, so the
+    deterministic variants route such a matrix or such an x to the atomic kernel (smvp_tjds_info_t.det_route == -1) and
+    the affected rows come out Inf / NaN exactly as the CSR kernels and the reference's loop produce them; rows that
+    the bad entries do not touch stay within 1e-12."""
+    rng = np.random.default_rng(21)
+    m, n, nnz = 3000, 2500, 40000
+    coo = util.random_coo(rng, m, n, nnz)
+    x = rng.uniform(-1, 1, n)
+
+    def check(coo, x):
+        rp, ci, va = oracle.csr_build(coo, m, n)
+        with np.errstate(invalid="ignore", over="ignore"):
+            y_ref = oracle.csr_mult(rp, ci, va, x)
+        good = np.isfinite(y_ref)
+        assert (~good).any() and good.any()
+        A = eng.CsrMatrix.build(coo, m, n)
+        yc, _ = A.mult(x, iters=1, variant=eng.CSR_MERGE)
+        A.free()
+        T = eng.TjdsMatrix.build(coo, m, n)
+        outs = [yc]
+        for variant in (eng.TJDS_ATOMIC, eng.TJDS_DETERMINISTIC, eng.TJDS_DETERMINISTIC_FAST):
+            y, _ = T.mult(x, iters=1, variant=variant)
+            outs.append(y)
+            if variant != eng.TJDS_ATOMIC:
+                assert T.plan()[1] == -1, "non-finite input must be routed away from the integer kernel"
+        T.free()
+        for y in outs:
+            assert np.array_equal(np.isnan(y), np.isnan(y_ref))
+            assert np.array_equal(np.isposinf(y), np.isposinf(y_ref)) and np.array_equal(np.isneginf(y), np.isneginf(y_ref))
+            assert util.rel_l2(y[good], y_ref[good]) <= TOL
+
+    bad = coo.copy()
+    bad["val"][17] = np.inf
+    bad["val"][4321] = -np.inf
+    bad["val"][999] = np.nan
+    check(bad, x)                      # non-finite matrix entries
+    xb = x.copy()
+    xb[5] = np.inf
+    xb[77] = np.nan
+    check(coo, xb)                     # non-finite x
+    # a finite x afterwards goes back to the integer kernel
+    T = eng.TjdsMatrix.build(coo, m, n)
+    T.mult(xb, iters=1, variant=eng.TJDS_DETERMINISTIC)
+    assert T.plan()[1] == -1
+    y, _ = T.mult(x, iters=1, variant=eng.TJDS_DETERMINISTIC)
+    assert T.plan()[1] == 1
+    assert util.rel_l2(y, oracle.csr_mult(*oracle.csr_build(coo, m, n), x)) <= TOL
+    T.free()
+
+
+def test_csr_hot_cold_split_forced(eng, monkeypatch):
+    """The hot / cold split of a relabelled handle (relabel.cu: csr_split_plan) on a small matrix with the prefix scaled
+    down: y within 1e-12 of the oracle through every entry point, the exported CSR arrays untouched, the vector kernel
+    and fan-out passes (which do not split) still right, empty rows / rows with only hot or only cold entries handled."""
+    import torch
+
+    monkeypatch.setenv("SMVP_CSR_RELABEL", "1")
+    monkeypatch.setenv("SMVP_CSR_SPLIT", "1")
+    monkeypatch.setenv("SMVP_HOT_L2", "3000")  # entries of x_rel that count as hot
+    rng = np.random.default_rng(91)
+    m, n = 50021, 40009
+    coo = _powerlaw_coo(rng, m, n, 700000, 4.0)
+    coo = coo[(coo["row"] % 97) != 5]  # some empty rows
+    x = rng.uniform(-1, 1, n)
+    rp, ci, va = oracle.csr_build(coo, m, n)
+    y_ref = oracle.csr_mult(rp, ci, va, x)
+    A = eng.CsrMatrix.build(coo, m, n)
+    for iters in (1, 3, 40):
+        y, _ = A.mult(x, iters=iters, variant=eng.CSR_MERGE)
+        assert util.rel_l2(y, y_ref) <= TOL, iters
+    assert A.x_relabel == 1 and A.x_split == 1
+    yv, _ = A.mult(x, iters=1, variant=eng.CSR_VECTOR)
+    assert util.rel_l2(yv, y_ref) <= TOL
+    g = A.export()
+    assert np.array_equal(g[0], rp) and np.array_equal(g[1], ci) and np.array_equal(g[2].view(np.int64), va.view(np.int64))
+    d_x = torch.as_tensor(x, device="cuda")
+    d_y = torch.full((m,), float("nan"), dtype=torch.float64, device="cuda")
+    A.set_x_device(d_x)
+    A.mult_device(None, d_y, eng.CSR_MERGE)
+    torch.cuda.synchronize()
+    assert util.rel_l2(d_y.cpu().numpy(), y_ref) <= TOL
+    outs = [torch.full((m,), float("nan"), dtype=torch.float64, device="cuda") for _ in range(2)]
+    A.mult_device_fanout(None, [o.data_ptr() for o in outs], eng.CSR_MERGE)
+    torch.cuda.synchronize()
+    assert util.rel_l2(outs[0].cpu().numpy(), y_ref) <= TOL and torch.equal(outs[0], outs[1])
+    A.free()
