@@ -219,6 +219,7 @@ int csr_relabel_plan(smvp_csr *A, cudaStream_t s)
     if (!use)
     {
         A->relabel_state = -1;
+        A->split_state = -1;
         return SMVP_OK;
     }
     A->x_order = order;
