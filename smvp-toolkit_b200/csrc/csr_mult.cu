@@ -1117,15 +1117,19 @@ static int env_int(const char *name, int dflt, int lo, int hi)
     return v < lo ? lo : (v > hi ? hi : v);
 }
 // defaults from the sweep on B200 (tools/sweep_e2e.py, profiles/): tuning hooks SMVP_PIPE_RANGES / SMVP_PIPE_XCHUNKS
-// The sweep found 32 ranges x 64 upload pieces best for a 402 MB vector: 12.6 MB per download piece, 6.3 MB per upload
-// piece, each piece costing ~23 us on its stream.  Smaller vectors (the row block of one GPU out of N) keep the PIECE
-// SIZE, not the piece count, so the fixed cost of a call shrinks with the block (round 1: e2e did not scale with N).
-constexpr int64_t PIPE_DOWN_PIECE_BYTES = 12 << 20;
+// Piece SIZE, not piece count, is fixed, so the fixed cost of a call shrinks with the block a rank owns (round 1: e2e did
+// not scale with N).  6 MB in both directions: on the 402 MB vectors of the 369^3 stencil that is 64 ranges x 64 upload
+// pieces, the best of every sweep (tools/sweep_e2e.py with SMVP_PIPE_TRACE=1, round 2: 9.8 ms per call against 12.2 ms
+// for 32 x 64 and 11.2 ms for 16 x 16 in the same run; the PCIe floor with both directions busy is 8.05 ms).  The trace
+// shows why the numbers scatter: with both directions busy the UPLOAD of the 402 MB ends anywhere between 8.3 and 11.5 ms
+// depending on how the pieces of the two directions interleave, equal-sized pieces interleave best.  Price: a pass cut
+// into 64 ranges spends 5.7 ms of GPU time instead of 2.7 (short launches), which is what ms_each reports for it.
+constexpr int64_t PIPE_DOWN_PIECE_BYTES = 6 << 20;
 constexpr int64_t PIPE_UP_PIECE_BYTES = 6 << 20;
 static int pipe_ranges(int64_t y_bytes)
 {
     const int64_t want = ceil_div64(y_bytes, PIPE_DOWN_PIECE_BYTES);
-    return env_int("SMVP_PIPE_RANGES", (int)(want < 2 ? 2 : (want > 32 ? 32 : want)), 1, PIPE_MAX_RANGES);
+    return env_int("SMVP_PIPE_RANGES", (int)(want < 2 ? 2 : (want > 64 ? 64 : want)), 1, PIPE_MAX_RANGES);
 }
 static int pipe_xchunks(int64_t x_bytes)
 {
@@ -1225,14 +1229,14 @@ struct PipeResources
 {
     cudaStream_t up[PIPE_MAX_STREAMS] = {}, down[PIPE_MAX_STREAMS] = {}, compute = nullptr;
     cudaEvent_t x_ready[PIPE_MAX_XCHUNKS] = {}, done[PIPE_MAX_RANGES] = {}, t0[PIPE_MAX_RANGES] = {}, t1[PIPE_MAX_RANGES] = {};
-    cudaEvent_t begin = nullptr;
+    cudaEvent_t begin = nullptr, down_done[PIPE_MAX_RANGES] = {};
     cudaError_t create()
     {
         // the pass runs on its own non-blocking stream: the legacy stream would serialise it against every other
         // blocking stream of the process
         cudaError_t e = cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking);
         if (e == cudaSuccess)
-            e = cudaEventCreateWithFlags(&begin, cudaEventDisableTiming);
+            e = cudaEventCreate(&begin);
         for (int k = 0; k < PIPE_MAX_STREAMS && e == cudaSuccess; k++)
         {
             e = cudaStreamCreateWithFlags(&up[k], cudaStreamNonBlocking);
@@ -1240,10 +1244,12 @@ struct PipeResources
                 e = cudaStreamCreateWithFlags(&down[k], cudaStreamNonBlocking);
         }
         for (int c = 0; c < PIPE_MAX_XCHUNKS && e == cudaSuccess; c++)
-            e = cudaEventCreateWithFlags(&x_ready[c], cudaEventDisableTiming);
+            e = cudaEventCreate(&x_ready[c]);
         for (int c = 0; c < PIPE_MAX_RANGES && e == cudaSuccess; c++)
         {
-            e = cudaEventCreateWithFlags(&done[c], cudaEventDisableTiming);
+            e = cudaEventCreate(&done[c]);
+            if (e == cudaSuccess)
+                e = cudaEventCreate(&down_done[c]);
             if (e == cudaSuccess)
                 e = cudaEventCreate(&t0[c]);
             if (e == cudaSuccess)
@@ -1264,6 +1270,8 @@ struct PipeResources
         {
             if (done[c])
                 cudaEventDestroy(done[c]);
+            if (down_done[c])
+                cudaEventDestroy(down_done[c]);
             if (t0[c])
                 cudaEventDestroy(t0[c]);
             if (t1[c])
@@ -1363,6 +1371,7 @@ static int csr_mult_pipelined(smvp_csr *A, const double *x_host, double *y_host,
             if (r1 > r0)
                 PIPE_CK(cudaMemcpyAsync(y_host + r0, A->d_y + r0, sizeof(double) * (size_t)(r1 - r0), cudaMemcpyDeviceToHost,
                                         R.down[c % NS]));
+            PIPE_CK(cudaEventRecord(R.down_done[c], R.down[c % NS]));
         }
     }
     // drain every stream of the pass, also after a failure (nothing may still touch the caller's buffers on return)
@@ -1388,6 +1397,21 @@ static int csr_mult_pipelined(smvp_csr *A, const double *x_host, double *y_host,
         total += t;
     }
     *ms = total;
+    if (getenv("SMVP_PIPE_TRACE")) // where the pass spends its time (ms after the start of the pass)
+    {
+        auto at = [&](cudaEvent_t ev) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, R.begin, ev);
+            return t;
+        };
+        fprintf(stderr, "[pipe] %d ranges, %d x pieces of %lld entries: ", NR, NX, (long long)xchunk);
+        if (x_host)
+            fprintf(stderr, "x piece 0 at %.3f, last x piece at %.3f | ", at(R.x_ready[0]), at(R.x_ready[NX - 1]));
+        fprintf(stderr, "range 0 computed at %.3f, last range at %.3f", at(R.t1[0]), at(R.t1[NR - 1]));
+        if (y_host)
+            fprintf(stderr, " | first rows down at %.3f, last rows down at %.3f", at(R.down_done[0]), at(R.down_done[NR - 1]));
+        fprintf(stderr, " ms\n");
+    }
     SMVP_CUDA(cudaGetLastError());
     return SMVP_OK;
 }
