@@ -1124,11 +1124,14 @@ static int env_int(const char *name, int dflt, int lo, int hi)
 // shows why the numbers scatter: with both directions busy the UPLOAD of the 402 MB ends anywhere between 8.3 and 11.5 ms
 // depending on how the pieces of the two directions interleave, equal-sized pieces interleave best.  Price: a pass cut
 // into 64 ranges spends 5.7 ms of GPU time instead of 2.7 (short launches), which is what ms_each reports for it.
-constexpr int64_t PIPE_DOWN_PIECE_BYTES = 6 << 20;
+// Shorter vectors (the row block of one GPU out of N) download in 12 MB pieces: 17 ranges x 33 upload pieces measured
+// 6.8 ms per call on the 201 MB blocks of 2 GPUs, 32 x 33 measured 7.95 ms.
+constexpr int64_t PIPE_DOWN_PIECE_BYTES = 12 << 20;
+constexpr int64_t PIPE_DOWN_PIECE_BYTES_LONG = 6 << 20; // vectors of 300 MB and more
 constexpr int64_t PIPE_UP_PIECE_BYTES = 6 << 20;
 static int pipe_ranges(int64_t y_bytes)
 {
-    const int64_t want = ceil_div64(y_bytes, PIPE_DOWN_PIECE_BYTES);
+    const int64_t want = ceil_div64(y_bytes, y_bytes >= (300ll << 20) ? PIPE_DOWN_PIECE_BYTES_LONG : PIPE_DOWN_PIECE_BYTES);
     return env_int("SMVP_PIPE_RANGES", (int)(want < 2 ? 2 : (want > 64 ? 64 : want)), 1, PIPE_MAX_RANGES);
 }
 static int pipe_xchunks(int64_t x_bytes)
