@@ -90,7 +90,9 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.interval = float(os.environ.get("SMVP_BENCH_SAMPLE_MS", "10")) * 1e-3
         self.stop_flag = threading.Event()
+        self.active = threading.Event()  # set for the duration of the timed region: only then are samples kept
         self.ok = False
         try:
             import pynvml
@@ -99,6 +101,9 @@ class ClockSampler(threading.Thread):
             pynvml.nvmlInit()
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            # first calls resolve the NVML entry points (milliseconds, under the GIL): done here, not in the timed region
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
             self.ok = True
         except Exception:
             self.ok = False
@@ -108,14 +113,16 @@ class ClockSampler(threading.Thread):
             return
         while not self.stop_flag.is_set():
             try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
                 r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                if self.active.is_set():
+                    self.samples.append(mhz)
+                    for bit, name in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(self.interval)
 
     def result(self):
         if not self.ok or not self.samples:
@@ -292,19 +299,25 @@ def timed_steps(ctx, op, steps, warmup, sample_clocks=True):
     CUDA events on the launching stream, MAX over ranks.  The SpMV launch of every step has its own event bracket
     (opened after any wait for the exchange of an earlier step)."""
     torch, stream = ctx.torch, ctx.stream
+    # the poller thread is started BEFORE the warm-up steps (its start-up costs the launching thread milliseconds of GIL and
+    # driver time: measured at 2 GPUs, 1.49 ms per step with the thread already running, 1.64 ms when it was started at
+    # the first timed step) and only keeps the samples it takes inside the timed region
+    # N > 1: only rank 0 polls NVML (its GPU's clocks are the ones reported).  A poll takes milliseconds inside the driver;
+    # with every rank polling, each one's hiccup reaches all ranks through the per-step barrier of the exchange
+    # (measured at 8 GPUs, tools/probe_steps.py: 0.628 ms per step without the pollers, 0.65 - 0.72 ms with 8 of them)
+    sampler = ClockSampler(ctx.local_rank) if (sample_clocks and ctx.rank == 0 and
+                                               os.environ.get("SMVP_BENCH_SAMPLE_MS") != "0") else None
+    if sampler:
+        sampler.start()
     for _ in range(max(warmup, 3)):
         op.step(stream)
     op.finish(stream)
     ctx.barrier()
-    # N > 1: only rank 0 polls NVML (its GPU's clocks are the ones reported).  A poll takes milliseconds inside the driver;
-    # with every rank polling, each one's hiccup reaches all ranks through the per-step barrier of the exchange
-    # (measured at 8 GPUs, tools/probe_steps.py: 0.628 ms per step without the pollers, 0.65 - 0.72 ms with 8 of them)
-    sampler = ClockSampler(ctx.local_rank) if (sample_clocks and ctx.rank == 0) else None
     launches0 = ctx.eng.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if sampler:
-        sampler.start()
+        sampler.active.set()
     e_begin.record(stream)
     for k in range(steps):
         op.spmv_events = ev[k]
@@ -315,6 +328,7 @@ def timed_steps(ctx, op, steps, warmup, sample_clocks=True):
     ctx.barrier()
     op.spmv_events = None
     if sampler:
+        sampler.active.clear()
         sampler.stop_flag.set()
         sampler.join()
     launches = ctx.eng.launch_count() - launches0
