@@ -333,9 +333,11 @@ def timed_steps(ctx, op, steps, warmup, sample_clocks=True):
         sampler.join()
     launches = ctx.eng.launch_count() - launches0
     total_ms = e_begin.elapsed_time(e_end)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    per_step = np.asarray([a.elapsed_time(b) for a, b in ev])
+    kern_ms = float(per_step.mean())
     total_max, kern_max = ctx.max_over_ranks([total_ms, kern_ms])
     return {"ms_per_step": total_max / steps, "kern_ms_local": kern_ms, "kern_ms_max": kern_max, "launches": int(launches),
+            "kern_ms_min": float(per_step.min()), "kern_ms_median": float(np.median(per_step)),
             "clocks": sampler.result() if sampler else None}
 
 
@@ -448,7 +450,8 @@ def perf_fields(ctx, t, global_bytes, local_bytes, nnz):
     return {"ms_per_step": ms, "value": value, "unit": UNIT, "gflops": 2 * nnz / (ms * 1e-3) / 1e9,
             "pct_of_hbm_peak_8000": 100.0 * value / 8000.0 / ctx.world,
             "frac_of_measured_peak": value / ctx.peak / ctx.world,
-            "kernel_ms": t["kern_ms_local"], "kernel_ms_max_over_ranks": t["kern_ms_max"],
+            "kernel_ms": t["kern_ms_local"], "kernel_ms_min": t["kern_ms_min"], "kernel_ms_median": t["kern_ms_median"],
+            "kernel_ms_max_over_ranks": t["kern_ms_max"],
             "kernel_frac_of_measured_peak": achieved / ctx.peak, "gpu_launches": t["launches"]}
 
 
@@ -632,7 +635,8 @@ def run_ours(args):
                 "traffic_source": ("profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch from the "
                                    "committed ncu --set full capture of this configuration (not measured in this run)"
                                    if traffic is not None else None),
-                "kernel": op.kernel_name, "kernel_ms": kern_ms,
+                "kernel": op.kernel_name, "kernel_ms": kern_ms, "kernel_ms_min": t["kern_ms_min"],
+                "kernel_ms_median": t["kern_ms_median"],
                 "kernel_ms_note": "CUDA events around the SpMV launch only, opened after any wait for an earlier step's exchange",
                 "algorithmic_bytes_per_launch": local_bytes, "peak_source": ctx.peak_src,
                 "frac_of_nominal_8000": achieved / 8000.0}

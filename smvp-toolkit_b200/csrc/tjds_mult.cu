@@ -31,7 +31,11 @@ namespace smvp
 #endif
 __device__ __forceinline__ int32_t ld_stream_i32(const int32_t *p)
 {
-#if SMVP_TJDS_STREAM
+#if SMVP_TJDS_STREAM == 2
+    int32_t v; // L2 fetches the whole 256-byte block the load falls into: a sequential stream finds its next lines in L2
+    asm volatile("ld.global.nc.L2::256B.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#elif SMVP_TJDS_STREAM
     int32_t v;
     asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
@@ -41,7 +45,11 @@ __device__ __forceinline__ int32_t ld_stream_i32(const int32_t *p)
 }
 __device__ __forceinline__ double ld_stream_f64(const double *p)
 {
-#if SMVP_TJDS_STREAM
+#if SMVP_TJDS_STREAM == 2
+    double v;
+    asm volatile("ld.global.nc.L2::256B.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+#elif SMVP_TJDS_STREAM
     double v;
     asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
