@@ -19,7 +19,9 @@
 // multiply puts them back (y[r] = y_rel[row_rank[r]]).
 //
 // When (AUTO): at least RELABEL_MIN_COLS indices of the space actually occur in the handle, and the RELABEL_HOT_COLS most
-// popular ones hold at least half of the nonzeros and at least four times their fair share AMONG THE OCCURRING ONES.  Banded and uniform matrices fail
+// popular ones hold at least half of the nonzeros and at least twice their fair share AMONG THE OCCURRING ONES (round 2:
+// "four times" could never hold for the row block of one GPU out of 4 or 8 of an R-MAT matrix -- it touches 12 - 20 Mi
+// columns, so the fair share of 4 Mi of them is already 0.2 - 0.35 -- and those blocks lost their relabelling).  Banded and uniform matrices fail
 // the test and keep their natural (already local, or hopeless) order.  SMVP_CSR_RELABEL / SMVP_TJDS_RELABEL = 1 / 0
 // force it on / off.
 #include "common.cuh"
@@ -164,7 +166,9 @@ int popularity_plan(const int32_t *d_idx, int64_t nnz, int32_t n, int forced, in
             SMVP_CUDA(cudaMemcpyAsync(&cover, d_cover, sizeof(cover), cudaMemcpyDeviceToHost, s));
             SMVP_CUDA(cudaStreamSynchronize(s));
             const double share = (double)cover / (double)nnz, fair = (double)k / (double)touched;
-            if (!(share >= 0.5 && share >= 4.0 * fair))
+            // skewed enough: the hot set holds most of the gathers AND at least twice what a flat distribution over the
+            // touched columns would give it (a banded block is exactly flat: share == fair)
+            if (!(share >= 0.5 && share >= 2.0 * fair))
                 return SMVP_OK;
         }
         SMVP_CUDA(dev_alloc(&order, n));
