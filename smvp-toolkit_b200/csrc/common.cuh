@@ -161,6 +161,7 @@ struct smvp_csr
     double *d_x, *d_y;
     // plan of the pipelined host-vector pass (csr_mult.cu): tile ranges, the rows each completes and how much of x
     // (a leading part, x arrives front to back) each reads.  Host-side copies; pipe_cfg = tile size they were cut for.
+    int32_t pipe_ramp;                       // 1: the ranges were cut with the ramped piece profile (SMVP_PIPE_PROFILE)
     int32_t pipe_cfg, pipe_ranges, pipe_xlo; // pipe_xlo: first entry of x any nonzero reads (rounded down to 64)
     int32_t pipe_tile[65], pipe_row[65], pipe_xneed[64];
     void *pipe_res; // streams and events of that pass, created on first use (csr_mult.cu)

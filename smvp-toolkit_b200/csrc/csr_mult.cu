@@ -1140,6 +1140,42 @@ static int pipe_xchunks(int64_t x_bytes)
     return env_int("SMVP_PIPE_XCHUNKS", (int)(want < 2 ? 2 : (want > 64 ? 64 : want)), 1, PIPE_MAX_XCHUNKS);
 }
 
+// Piece boundaries as fractions of the whole (f[0] = 0 ... f[n] = 1).  SMVP_PIPE_PROFILE=ramp (tuning hook): small pieces at
+// both ends, large ones in the middle -- 2, 4, 8, 16 MB, then 24 MB pieces, then 16, 8, 4, 2 MB.  The first range can start
+// (and the first rows go down) after 2 MB instead of 6, the tail after the last upload is one 2 MB piece, and the long
+// middle uses transfers large enough for both PCIe directions to run near their rate.  MEASURED: it loses -- 10.9 ms per call
+// against 9.8 ms for 64 x 64 equal 6 MB pieces in the same run (the upload ends at 9.9 instead of 9.2 ms: with both
+// directions busy, many small equal pieces interleave better than a few large ones).  Default: n equal pieces.
+static int pipe_profile(int64_t bytes, int n_uniform, int max_pieces, double *f)
+{
+    const char *pe = getenv("SMVP_PIPE_PROFILE");
+    const bool ramp = pe && pe[0] == 'r';
+    const int64_t MB = 1 << 20;
+    const int64_t ends[4] = {2 * MB, 4 * MB, 8 * MB, 16 * MB};
+    const int64_t big = 24 * MB, ends_sum = 2 * (2 + 4 + 8 + 16) * MB;
+    int n = 0;
+    if (ramp && bytes >= ends_sum + 2 * big)
+    {
+        const int64_t mid = bytes - ends_sum;
+        int nmid = (int)ceil_div64(mid, big);
+        if (8 + nmid > max_pieces)
+            nmid = max_pieces - 8;
+        double at = 0.0;
+        f[n++] = 0.0;
+        for (int i = 0; i < 4; i++)
+            f[n++] = (at += (double)ends[i] / (double)bytes);
+        for (int i = 0; i < nmid; i++)
+            f[n++] = (at += (double)mid / nmid / (double)bytes);
+        for (int i = 3; i >= 0; i--)
+            f[n++] = (at += (double)ends[i] / (double)bytes);
+        f[n - 1] = 1.0;
+        return n - 1;
+    }
+    for (int i = 0; i <= n_uniform; i++)
+        f[i] = (double)i / n_uniform;
+    return n_uniform;
+}
+
 // largest and smallest column index among nonzeros [n0, n1): out[0] = max (start -1), out[1] = min (start INT32_MAX)
 __global__ void __launch_bounds__(256) col_range_kernel(const int32_t *__restrict__ col_ind, int64_t n0, int64_t n1,
                                                         int32_t *__restrict__ out)
@@ -1167,9 +1203,13 @@ __global__ void __launch_bounds__(256) col_range_kernel(const int32_t *__restric
 static int pipe_plan(smvp_csr *A)
 {
     SMVP_TRY(merge_plan(A, pick_merge_cfg(A), 0));
-    const int NR = pipe_ranges(8 * (int64_t)A->rows);
-    if (A->pipe_cfg == A->merge_cfg && A->pipe_ranges == NR)
+    double rf[PIPE_MAX_RANGES + 1];
+    const int NR = pipe_profile(8 * (int64_t)A->rows, pipe_ranges(8 * (int64_t)A->rows), PIPE_MAX_RANGES, rf);
+    const char *pe = getenv("SMVP_PIPE_PROFILE");
+    const int ramp = pe && pe[0] == 'r' ? 1 : 0;
+    if (A->pipe_cfg == A->merge_cfg && A->pipe_ranges == NR && A->pipe_ramp == ramp)
         return SMVP_OK;
+    A->pipe_ramp = ramp;
     const int32_t T = A->merge_tiles;
     const int64_t tile_items = A->merge_cfg;
     int32_t *d_max = nullptr; // per range: {largest, smallest} column index
@@ -1183,7 +1223,7 @@ static int pipe_plan(smvp_csr *A)
     cudaError_t e = cudaMemcpy(d_max, h_max, sizeof(h_max), cudaMemcpyHostToDevice);
     for (int c = 0; c <= NR && e == cudaSuccess; c++)
     {
-        A->pipe_tile[c] = (int32_t)((int64_t)T * c / NR);
+        A->pipe_tile[c] = c == NR ? T : (int32_t)((double)T * rf[c]);
         // rows consumed before each boundary tile (tile_row[T] = rows)
         e = cudaMemcpy(&A->pipe_row[c], A->tile_row + A->pipe_tile[c], sizeof(int32_t), cudaMemcpyDeviceToHost);
     }
@@ -1322,8 +1362,14 @@ static int csr_mult_pipelined(smvp_csr *A, const double *x_host, double *y_host,
     const int NR = A->pipe_ranges, NS = pipe_streams();
     const int64_t xlo = A->pipe_xlo, xhi = NR > 0 ? A->pipe_xneed[NR - 1] : 0;
     const int64_t xlen = xhi > xlo ? xhi - xlo : 0;
-    const int NX = pipe_xchunks(8 * xlen);
-    const int64_t xchunk = ((ceil_div64(xlen > 0 ? xlen : 1, NX) + 63) / 64) * 64; // entries per upload piece (512 B multiple)
+    double xf[PIPE_MAX_XCHUNKS + 1];
+    const int NX = pipe_profile(8 * xlen, pipe_xchunks(8 * xlen), PIPE_MAX_XCHUNKS, xf);
+    int64_t xb[PIPE_MAX_XCHUNKS + 1]; // piece k uploads x[xb[k], xb[k+1]) (boundaries on 512-byte multiples)
+    for (int k = 0; k <= NX; k++)
+    {
+        int64_t at = xlo + (((int64_t)((double)xlen * xf[k]) + 63) / 64) * 64;
+        xb[k] = (k == NX || at > xhi) ? xhi : at;
+    }
     cudaStream_t cs = R.compute;
     // first failing runtime call of the pass; later calls are skipped, the streams are still drained below
 #define PIPE_CK(expr)            \
@@ -1344,7 +1390,7 @@ static int csr_mult_pipelined(smvp_csr *A, const double *x_host, double *y_host,
     {
         for (int k = 0; k < NX; k++)
         {
-            const int64_t a = xlo + (int64_t)k * xchunk, b = a + xchunk < xhi ? a + xchunk : xhi;
+            const int64_t a = xb[k], b = xb[k + 1];
             if (b > a)
                 PIPE_CK(cudaMemcpyAsync(A->d_x + a, x_host + a, sizeof(double) * (size_t)(b - a), cudaMemcpyHostToDevice, R.up[k % NS]));
             PIPE_CK(cudaEventRecord(R.x_ready[k], R.up[k % NS]));
@@ -1357,8 +1403,9 @@ static int csr_mult_pipelined(smvp_csr *A, const double *x_host, double *y_host,
     {
         if (x_host && A->pipe_xneed[c] > xlo)
         {
-            int k = (int)(((int64_t)A->pipe_xneed[c] - 1 - xlo) / xchunk);
-            k = k < NX ? k : NX - 1;
+            int k = waited < 0 ? 0 : waited; // first piece whose end covers what the range reads
+            while (k < NX - 1 && xb[k + 1] < (int64_t)A->pipe_xneed[c])
+                k++;
             for (; waited < k; waited++) // pieces alternate over NS streams: wait for each one up to k
                 PIPE_CK(cudaStreamWaitEvent(cs, R.x_ready[waited + 1], 0));
         }
@@ -1407,7 +1454,8 @@ static int csr_mult_pipelined(smvp_csr *A, const double *x_host, double *y_host,
             cudaEventElapsedTime(&t, R.begin, ev);
             return t;
         };
-        fprintf(stderr, "[pipe] %d ranges, %d x pieces of %lld entries: ", NR, NX, (long long)xchunk);
+        fprintf(stderr, "[pipe] %d ranges, %d x pieces (first %lld, largest %lld entries): ", NR, NX, (long long)(xb[1] - xb[0]),
+                (long long)(NX > 4 ? xb[NX / 2 + 1] - xb[NX / 2] : xb[1] - xb[0]));
         if (x_host)
             fprintf(stderr, "x piece 0 at %.3f, last x piece at %.3f | ", at(R.x_ready[0]), at(R.x_ready[NX - 1]));
         fprintf(stderr, "range 0 computed at %.3f, last range at %.3f", at(R.t1[0]), at(R.t1[NR - 1]));

@@ -30,8 +30,15 @@ for setting in ["off"] + args.settings.split(","):
         os.environ["SMVP_NO_OVERLAP"] = "1"
     else:
         os.environ.pop("SMVP_NO_OVERLAP", None)
-        r, xc, ns = (setting.split("x") + ["2"])[:3]
-        os.environ["SMVP_PIPE_RANGES"], os.environ["SMVP_PIPE_XCHUNKS"], os.environ["SMVP_PIPE_STREAMS"] = r, xc, ns
+        if setting == "ramp":
+            os.environ["SMVP_PIPE_PROFILE"] = "ramp"
+            for k in ("SMVP_PIPE_RANGES", "SMVP_PIPE_XCHUNKS"):
+                os.environ.pop(k, None)
+            os.environ["SMVP_PIPE_STREAMS"] = "1"
+        else:
+            os.environ.pop("SMVP_PIPE_PROFILE", None)
+            r, xc, ns = (setting.split("x") + ["2"])[:3]
+            os.environ["SMVP_PIPE_RANGES"], os.environ["SMVP_PIPE_XCHUNKS"], os.environ["SMVP_PIPE_STREAMS"] = r, xc, ns
     ms = ctypes.c_double(0)
     for it in range(2 + args.steps):
         if it == 2:
