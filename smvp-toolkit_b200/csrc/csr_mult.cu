@@ -282,22 +282,27 @@ __global__ void __launch_bounds__(256) csr_vector_kernel(const int32_t *__restri
 constexpr int TINY_THREADS = 512;
 constexpr int64_t TINY_MAX_NNZ = 16384;
 constexpr int32_t TINY_MAX_ROWS = 4096;
+template <int LPR> // lanes per row: 4 / 8 / 16 / 32 from the mean row length, so that few rounds cover all rows
 __global__ void __launch_bounds__(TINY_THREADS) csr_tiny_loop_kernel(const int32_t *row_ptr, const int32_t *col_ind, const double *val,
                                                                      const double *x, double *y, int32_t rows, int passes)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x % LPR, group = threadIdx.x / LPR;
     for (int p = 0; p < passes; p++)
     {
-        for (int32_t row = warp; row < rows; row += TINY_THREADS / 32)
+        for (int32_t row0 = 0; row0 < rows; row0 += TINY_THREADS / LPR) // every thread takes part in the shuffles
         {
-            const int32_t start = row_ptr[row], end = row_ptr[row + 1];
+            const int32_t row = row0 + group;
             double sum = 0.0;
-            for (int32_t j = start + lane; j < end; j += 32)
-                sum = __dadd_rn(sum, __dmul_rn(val[j], x[col_ind[j]]));
+            if (row < rows)
+            {
+                const int32_t start = row_ptr[row], end = row_ptr[row + 1];
+                for (int32_t j = start + lane; j < end; j += LPR)
+                    sum = __dadd_rn(sum, __dmul_rn(val[j], x[col_ind[j]]));
+            }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
+            for (int o = LPR / 2; o > 0; o >>= 1)
                 sum = __dadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
-            if (lane == 0)
+            if (row < rows && lane == 0)
                 y[row] = sum;
         }
         __syncthreads(); // pass boundary: also a compiler barrier, the next pass reloads everything
@@ -1526,8 +1531,19 @@ extern "C" int smvp_csr_mult(smvp_csr *A, const double *x_host, double *y_host, 
         std::function<int(cudaStream_t, int)> multi;
         if (tiny)
             multi = [&](cudaStream_t s, int n) {
-                SMVP_LAUNCH(csr_tiny_loop_kernel, 1, TINY_THREADS, 0, s, (const int32_t *)A->row_ptr, mult_cols(A), (const double *)A->val,
-                            xm, A->d_y, A->rows, n);
+                const double mean = A->rows > 0 ? (double)A->nnz / A->rows : 0.0;
+#define SMVP_TINY(L)                                                                                                              \
+    SMVP_LAUNCH(csr_tiny_loop_kernel<L>, 1, TINY_THREADS, 0, s, (const int32_t *)A->row_ptr, mult_cols(A), (const double *)A->val, xm, \
+                A->d_y, A->rows, n)
+                if (mean <= 4.5)
+                    SMVP_TINY(4);
+                else if (mean <= 9.0)
+                    SMVP_TINY(8);
+                else if (mean <= 18.0)
+                    SMVP_TINY(16);
+                else
+                    SMVP_TINY(32);
+#undef SMVP_TINY
                 SMVP_CUDA(cudaGetLastError());
                 return (int)SMVP_OK;
             };
