@@ -215,8 +215,9 @@ struct smvp_tjds
     double *d_x, *d_y;
     // popularity relabelling of the ROW space (relabel.cu): 0 undecided, 1 in use, -1 not worth it
     int32_t skew;            // walk of the multiply kernels: 0 undecided, 1 skewed (runs of equal rows), -1 straight
-    int32_t det_flags[3];    // host copy: [0] bit 0 = the matrix holds Inf/NaN, bit 1 = a row has entries but only zeros;
-                             // [1] / [2] = largest / smallest row_exp (EXP_NONE / EXP_LOW_NONE if none)
+    int32_t det_flags[5];    // host copy: [0] bit 0 = the matrix holds Inf/NaN, bit 1 = a row has entries but only zeros;
+                             // [1] / [2] = largest / smallest row_exp (EXP_NONE / EXP_LOW_NONE if none);
+                             // [3] / [4] = first / last row (of the index space the kernels use) that holds an entry
     int32_t *x_exp_host;     // pinned: x_exp as of the last smvp_tjds_set_x_device, valid once x_exp_event has passed
     cudaEvent_t x_exp_event;
     int32_t x_exp_pending;   // 1: x_exp_host has not been looked at since the last set_x

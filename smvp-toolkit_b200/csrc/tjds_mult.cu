@@ -275,10 +275,13 @@ __global__ void __launch_bounds__(256) tjds_row_bound_kernel(const int32_t *__re
                                                              int32_t *__restrict__ flags)
 {
     bool bad = false;
+    int32_t rmin = 0x7fffffff, rmax = -1;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += (int64_t)gridDim.x * blockDim.x)
     {
         const int32_t r = row_ind[j];
         const double v = val[j];
+        rmin = min(rmin, r);
+        rmax = max(rmax, r);
         atomicAdd(row_cnt + r, 1u);
         if (!isfinite(v))
             bad = true;
@@ -287,6 +290,17 @@ __global__ void __launch_bounds__(256) tjds_row_bound_kernel(const int32_t *__re
     }
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0)
         atomicOr(flags, 1); // flags[0] bit 0: the matrix holds an Inf or NaN
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        rmin = min(rmin, __shfl_xor_sync(0xffffffffu, rmin, o));
+        rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+    }
+    if ((threadIdx.x & 31) == 0 && rmax >= 0)
+    {
+        atomicMin(flags + 3, rmin); // flags[3], flags[4]: first / last row that holds an entry (the column block of one GPU
+        atomicMax(flags + 4, rmax); // out of N of a banded matrix touches ~1/N of the rows)
+    }
 }
 
 __global__ void __launch_bounds__(256) tjds_row_exp_kernel(int32_t *__restrict__ row_exp, const uint32_t *__restrict__ row_cnt, int32_t rows,
@@ -507,12 +521,18 @@ __global__ void __launch_bounds__(256, MINB) tjds_det_kernel(const int2 *__restr
 // row_rank != NULL: the accumulators and row_exp are in popularity-rank order (relabelled handle), y is not
 __global__ void __launch_bounds__(256) tjds_det_finalize_kernel(const long long *__restrict__ acc, const int32_t *__restrict__ row_exp,
                                                                 const int32_t *__restrict__ x_exp, int32_t rows, double *__restrict__ y,
-                                                                const int32_t *__restrict__ row_rank, int words)
+                                                                const int32_t *__restrict__ row_rank, int words, int32_t r_lo, int32_t r_hi)
 {
+    // accumulators exist (are cleared and filled) only for rows [r_lo, r_hi) of the index space the kernels use
     const int32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows)
         return;
     const int32_t r = row_rank ? row_rank[row] : row;
+    if (r < r_lo || r >= r_hi)
+    {
+        y[row] = 0.0;
+        return;
+    }
     longlong2 a;
     a.x = acc[r];
     a.y = words == 2 ? acc[(int64_t)rows + r] : 0; // one word: the value is hi * 2^(T - 62), i.e. lo = 0 below
@@ -611,8 +631,8 @@ static int tjds_prepare_det(smvp_tjds *A, cudaStream_t s)
         SMVP_CUDA(dev_alloc(&row_exp, A->rows));
         SMVP_CUDA(dev_alloc(&acc, 2 * (int64_t)A->rows));
         SMVP_CUDA(cnt.alloc<uint32_t>(A->rows));
-        SMVP_CUDA(flags.alloc<int32_t>(3));
-        const int32_t h0[3] = {0, EXP_NONE, EXP_LOW_NONE};
+        SMVP_CUDA(flags.alloc<int32_t>(5));
+        const int32_t h0[5] = {0, EXP_NONE, EXP_LOW_NONE, 0x7fffffff, -1};
         SMVP_CUDA(cudaMemcpyAsync(flags.p, h0, sizeof(h0), cudaMemcpyHostToDevice, s));
         SMVP_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(uint32_t) * (size_t)A->rows, s));
         // EXP_NONE = 0x80808080 is a byte pattern, so a memset fills it
@@ -630,6 +650,7 @@ static int tjds_prepare_det(smvp_tjds *A, cudaStream_t s)
             SMVP_LAUNCH(tjds_row_exp_kernel, (unsigned)ceil_div64(A->rows, 256), 256, 0, s, row_exp, (const uint32_t *)cnt.as<uint32_t>(),
                         A->rows, flags.as<int32_t>());
         SMVP_CUDA(cudaMemcpyAsync(A->det_flags, flags.p, sizeof(A->det_flags), cudaMemcpyDeviceToHost, s));
+        static_assert(sizeof(A->det_flags) == 5 * sizeof(int32_t), "flags layout");
         SMVP_CUDA(cudaStreamSynchronize(s));
         SMVP_CUDA(cudaGetLastError());
         return SMVP_OK;
@@ -771,7 +792,10 @@ static int tjds_pass(smvp_tjds *A, double *d_y, int variant, int32_t diag_limit,
     else
     {
         const int words = variant == SMVP_TJDS_DETERMINISTIC_FAST ? 1 : 2;
-        SMVP_CUDA(cudaMemsetAsync(A->acc, 0, sizeof(long long) * (size_t)words * (size_t)A->rows, s));
+        // only the rows that hold entries have accumulators to clear and convert (tjds_prepare_det found the range)
+        const int32_t r_lo = A->det_flags[4] >= 0 ? A->det_flags[3] : 0, r_hi = A->det_flags[4] + 1;
+        for (int w = 0; w < words && r_hi > r_lo; w++)
+            SMVP_CUDA(cudaMemsetAsync(A->acc + (size_t)w * (size_t)A->rows + r_lo, 0, sizeof(long long) * (size_t)(r_hi - r_lo), s));
         if (blocks > 0 && lim > 0)
         {
 #define SMVP_DET_LAUNCH(U, SK, FA, MB, MB1)                                                                                       \
@@ -808,7 +832,7 @@ static int tjds_pass(smvp_tjds *A, double *d_y, int variant, int32_t diag_limit,
         }
         SMVP_LAUNCH(tjds_det_finalize_kernel, (unsigned)ceil_div64(A->rows, 256), 256, 0, s, (const long long *)A->acc,
                     (const int32_t *)A->row_exp, (const int32_t *)A->x_exp, A->rows, d_y,
-                    ranked ? (const int32_t *)A->row_rank : nullptr, words);
+                    ranked ? (const int32_t *)A->row_rank : nullptr, words, r_lo, r_hi);
     }
     SMVP_CUDA(cudaGetLastError());
     return SMVP_OK;
