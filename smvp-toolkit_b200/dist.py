@@ -356,13 +356,19 @@ class RowBlockCsr:
         "tma_unicast": "%d one-warp CTAs driving the TMA engine (cp.async.bulk global->shared->global): my rows are read once "
                        "and leave for every peer's y as bulk stores over NVLink",
         "tma_multicast": "%d one-warp CTAs driving the TMA engine (cp.async.bulk) with bulk stores to the NVSwitch multicast address",
+        "tma_hybrid": "%d one-warp CTAs driving the TMA engine: the first half of my rows goes to the NVSwitch multicast address, "
+                      "the second half to every peer by unicast (less ingress than all-multicast, less egress than all-unicast)",
     }
 
     def _setup_pipeline(self):
         import torch
 
         nloc = self.r1 - self.r0
-        self.y_src = [torch.zeros(nloc, dtype=torch.float64, device="cuda") for _ in range(self.nbuf)]
+        # staging buffers of the multicast schemes: each starts on the same 16-byte phase as its destination
+        # y_sym[b * M + r0] (M and r0 may be odd), otherwise the TMA push (bulk copies need source and destination on
+        # the same phase) would fall back to the 512-thread store kernel for half of the (rank, buffer) pairs
+        self._y_src_raw = [torch.zeros(nloc + 2, dtype=torch.float64, device="cuda") for _ in range(self.nbuf)]
+        self.y_src = [self._y_src_raw[b][((b * self.M + self.r0) & 1):][:nloc] for b in range(self.nbuf)]
         self.peer_views = [self.symm.get_buffer(k, (self.nbuf * self.M,), torch.float64) for k in self.peer_ranks]
         self.peer_ptrs = [int(self.symm.buffer_ptrs[k]) for k in self.peer_ranks]
         self.push_stream = torch.cuda.Stream(priority=-1)
@@ -379,14 +385,14 @@ class RowBlockCsr:
         self._scheme_forced = forced is not None
 
     def scheme_candidates(self):
-        c = ["ce_unicast", "tma_unicast:32", "tma_unicast:64", "tma_unicast:128", "sm_unicast:32"]
+        c = ["ce_unicast", "tma_unicast:16", "tma_unicast:32", "tma_unicast:64", "tma_unicast:128", "sm_unicast:32"]
         if self.mc_base:
-            c += ["ce_multicast", "sm_multicast:32", "tma_multicast:32", "tma_multicast:64"]
+            c += ["ce_multicast", "sm_multicast:32", "tma_multicast:32", "tma_multicast:64", "tma_multicast:128", "tma_hybrid:64"]
         return c
 
     def set_scheme(self, scheme):
         kind, _, arg = scheme.partition(":")
-        if kind not in self.SCHEME_HOW or (kind.endswith("multicast") and not self.mc_base):
+        if kind not in self.SCHEME_HOW or ((kind.endswith("multicast") or kind == "tma_hybrid") and not self.mc_base):
             raise ValueError("unknown or unavailable pipeline scheme %r" % scheme)
         self.scheme, self.scheme_kind, self.scheme_ctas = scheme, kind, int(arg or 0)
         # a push done by a kernel runs BESIDE the next step's SpMV: the persistent merge-path grid leaves one CTA slot
@@ -470,7 +476,7 @@ class RowBlockCsr:
         """Where the SpMV of buffer b writes my rows, and what the push reads.  Unicast schemes: straight into my own copy
         of y (my rows need no transfer to myself).  Multicast schemes: a private staging buffer -- the switch writes my
         rows into EVERY rank's y, mine included, and must not race with the kernel that produces them."""
-        if self.scheme_kind.endswith("multicast"):
+        if self.scheme_kind.endswith("multicast") or self.scheme_kind == "tma_hybrid":
             return self.y_src[b]
         return self.y_sym[b * self.M + self.r0:b * self.M + self.r1]
 
@@ -502,6 +508,14 @@ class RowBlockCsr:
             self.eng.push_tma_device([self.mc_base + off], src, nbytes, self.scheme_ctas, ps)
         elif self.scheme_kind == "tma_unicast":
             self.eng.push_tma_device([p + off for p in self.peer_ptrs], src, nbytes, self.scheme_ctas, ps)
+        elif self.scheme_kind == "tma_hybrid":
+            half = ((self.r1 - self.r0) // 2) & ~1  # rows; even: the second part stays 16-byte aligned
+            hb = 8 * half
+            if hb > 0:
+                self.eng.push_tma_device([self.mc_base + off], src, hb, max(self.scheme_ctas // 2, 1), ps)
+            if nbytes > hb:  # second half: every peer and my own copy of y (the staging buffer is not y)
+                dsts = [p + off + hb for p in self.peer_ptrs] + [int(self.symm.buffer_ptrs[self.rank]) + off + hb]
+                self.eng.push_tma_device(dsts, src[half:], nbytes - hb, max(self.scheme_ctas // 2, 1), ps)
         else:  # sm_unicast: one kernel reads my rows once and stores them into every peer's buffer
             self.eng.push_fanout_device([p + off for p in self.peer_ptrs], src, nbytes, self.scheme_ctas, ps)
         with torch.cuda.stream(ps):
@@ -701,7 +715,7 @@ class RowBlockCsr:
     def free(self):
         for A in self.subs:
             A.free()
-        self.y_full = self.y_local = self.peer_views = self.y_sym = self.y_src = self.y_pad = None
+        self.y_full = self.y_local = self.peer_views = self.y_sym = self.y_src = self._y_src_raw = self.y_pad = None
 
 
 class ColBlockTjds:

@@ -36,7 +36,7 @@ def main():
         dist.barrier()
         ok = True
         for k in range(world):
-            if k == rank and not scheme.split(":")[0].endswith("multicast"):
+            if k == rank and scheme.split(":")[0].endswith("unicast"):
                 continue  # unicast schemes do not send my rows to myself
             exp = torch.arange(op.bounds[k], op.bounds[k + 1], dtype=torch.float64, device="cuda") * 0.5 + 1000.0 * (k + 1)
             ok = ok and bool(torch.equal(op.y_sym[op.bounds[k]:op.bounds[k + 1]], exp))
