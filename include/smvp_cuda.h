@@ -99,7 +99,13 @@ int smvp_tjds_build(const smvp_coo *coo, int32_t rows, int32_t cols, int64_t nnz
  * (main-cli.c:405 vs :408/:419).  x is copied to the device once and y copied back once per call
  * (the reference reports the last iteration's y).  For vectors of millions of entries smvp_csr_mult overlaps
  * both copies with the first / last pass, and uploads only the part of x between the smallest and the largest
- * column index the matrix holds (the rest is never read): page-locked host buffers make the overlap effective.
+ * column index the matrix holds (the rest is never read) -- when BOTH vectors are page-locked (smvp_host_alloc,
+ * cudaHostAlloc, cudaHostRegister); pageable buffers are served by plain copies (an asynchronous copy from pageable
+ * memory blocks the host, which would serialise the pieces).  ms_each of such a pass is the sum of the device
+ * brackets of its tile ranges (short launches: more GPU time than one whole-matrix launch).
+ * Small matrices (rows + cols + nnz < 2^22): the loop runs batched -- one untimed pass, one pass timed exactly, the
+ * others replayed from CUDA graphs 50 at a time (a pass is charged its batch's time / 50); SMVP_EXACT_ITER_TIMES=1
+ * restores one event pair and one synchronisation per iteration.
  * smvp_tjds_mult: diag_limit <= 0 walks every jagged diagonal.  diag_limit = k > 0 walks only the
  * first k (and, like the shipped loop, skips a final diagonal that holds a single element): with
  * k = smvp_tjds_info().ref_diag_limit this reproduces the reference's golden TJDS report files,
