@@ -65,6 +65,13 @@ def _worker(rank, world, port, name, out):
                                       ordered=True)
         assert torch.equal(owned2, owned3), "rank-ordered combine must be bit-identical run to run"
         err_tjds = max(err_tjds, float(np.linalg.norm(owned2.numpy()[: hi - lo] - y_ref[lo:hi]) / np.linalg.norm(y_ref)))
+        # the NCCL-baseline wiring: ONE all-gather on equal padded slots + compaction into the contiguous y
+        per = max(rb[g + 1] - rb[g] for g in range(world))
+        y_pad = torch.full((per * world,), float("nan"), dtype=torch.float64)
+        y_pad[rank * per:rank * per + (r1 - r0)] = torch.from_numpy(oracle.csr_mult(*arrays, x.numpy()))
+        y_full2 = torch.full((m,), float("nan"), dtype=torch.float64)
+        sdist.allgather_padded(dist, y_pad, y_full2, rb, rank, per)
+        assert torch.equal(y_full2, y_full), "padded all-gather + compaction must reproduce the block-wise all-gather"
         nnz_share = len(blk) / max(len(coo), 1)
         out[rank] = (err_csr, err_tjds, nnz_share, rb, cb)
     finally:
